@@ -1,0 +1,419 @@
+// scp_b200.cu -- CUDA kernels (sm_100a) and the C ABI of include/scp_b200.h.
+//
+// Kernels
+//   scp_solve_kernel      persistent, one CTA per resident scenario, scenarios
+//                         handed out by an atomic counter; runs the whole SCP
+//                         loop of scp.py:131-180 on device (scp_device.inl).
+//   scp_reconstruct_kernel  scp.py:371-397 / 559-595 as warp-level prefix scans.
+//   scp_linearize_kernel    scp.py:453-557 matrix free + scp.py:597-615 reduction.
+// No CPU fallback: every entry point needs a CUDA device.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/scp_b200.h"
+#include "scp_defaults.h"
+#include "scp_device.inl"
+#include "scp_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(100 + (int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+constexpr int SOLVE_THREADS = 512;
+constexpr size_t SMEM_BASE = 4 * scp::RED * sizeof(double);
+constexpr size_t SMEM_NMAT_LIMIT = 160 * 1024;
+
+size_t nmat_smem_bytes(int K) {
+  size_t b = (size_t)K * K * sizeof(double);
+  return b <= SMEM_NMAT_LIMIT ? b : 0;
+}
+
+size_t slot_bytes(const scp::Layout& L) { return L.n_double * sizeof(double) + L.n_int * sizeof(int); }
+
+int validate(const scp_b200_problem* p) {
+  if (!p) return fail(1, "null problem");
+  if (p->n_agents < 1) return fail(1, "n_agents must be >= 1");
+  if (p->n_steps < 2) return fail(1, "n_steps must be >= 2");
+  if (2 * p->n_steps > scp::RED) return fail(1, "n_steps must be <= 512");
+  if (!(p->time_step > 0)) return fail(1, "time_step must be > 0");
+  if (p->max_scp_iter < 0 || p->max_scp_iter > SCP_B200_MAX_SCP_ITER) return fail(1, "max_scp_iter out of range");
+  if (p->check_every < 1 || p->max_admm_iter < 1) return fail(1, "bad ADMM iteration settings");
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- solver kernel
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
+                 const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
+                 double* ws_d, int* ws_i, double* acc, double* pos, double* vel, scp_b200_record* rec,
+                 unsigned int* counter, int nmat_in_smem) {
+  extern __shared__ double smem[];
+  __shared__ int s_b;
+  scp::Ctx c;
+  c.nthreads = blockDim.x;
+  c.N = g.pb.n_agents; c.K = g.pb.n_steps; c.Q = 2 * c.N;
+  c.g = &g;
+  c.wd = ws_d + (size_t)blockIdx.x * g.L.n_double;
+  c.wi = ws_i + (size_t)blockIdx.x * g.L.n_int;
+  c.sm = smem;
+  c.nmat = nullptr;
+  c.nmat_in_smem = nmat_in_smem;
+  for (;;) {
+    if (threadIdx.x == 0) s_b = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int b = s_b;
+    __syncthreads();
+    if (b >= B) break;
+    const size_t s2 = (size_t)b * c.N * 2, s3 = (size_t)b * c.N * c.K * 2;
+    c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
+    c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
+    scp::solve_scenario(c);
+  }
+}
+
+// ---------------------------------------------------------------------------------- reconstruct
+// One warp per (scenario, agent); lanes stride over k with double2 (x,y) loads, the
+// running sums c1 = cumsum(a), c2 = cumsum(c1) are carried by a 2-state warp scan:
+//   v[k+1] = v0 + h c1[k],  p[k+1] = p0 + h (k+1) v0 + h^2 (c2[k] - c1[k]/2)   
+__global__ void __launch_bounds__(256)
+scp_reconstruct_kernel(const double2* __restrict__ acc, const double2* __restrict__ p0,
+                       const double2* __restrict__ v0, int BN, int K, double h, double2* __restrict__ pos,
+                       double2* __restrict__ vel) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= BN) return;
+  const double2* a = acc + (size_t)warp * K;
+  double2* po = pos + (size_t)warp * K;
+  double2* ve = vel + (size_t)warp * K;
+  const double2 P0 = p0[warp], V0 = v0[warp];
+  if (lane == 0) { po[0] = P0; ve[0] = V0; }
+  double c1x = 0, c1y = 0, c2x = 0, c2y = 0;   // carries
+  for (int base = 0; base < K - 1; base += 32) {
+    const int k = base + lane;
+    double2 v = make_double2(0.0, 0.0);
+    if (k < K - 1) v = a[k];
+    double s1x = v.x, s1y = v.y, s2x = v.x, s2y = v.y;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double o1x = __shfl_up_sync(0xffffffffu, s1x, d), o1y = __shfl_up_sync(0xffffffffu, s1y, d);
+      double o2x = __shfl_up_sync(0xffffffffu, s2x, d), o2y = __shfl_up_sync(0xffffffffu, s2y, d);
+      if (lane >= d) {
+        s2x += o2x + (double)d * o1x; s2y += o2y + (double)d * o1y;
+        s1x += o1x; s1y += o1y;
+      }
+    }
+    const double n = (double)(lane + 1);
+    const double t2x = c2x + n * c1x + s2x, t2y = c2y + n * c1y + s2y;
+    const double t1x = c1x + s1x, t1y = c1y + s1y;
+    if (k < K - 1) {
+      const double kk = (double)(k + 1);
+      ve[k + 1] = make_double2(V0.x + h * t1x, V0.y + h * t1y);
+      po[k + 1] = make_double2(P0.x + h * kk * V0.x + h * h * (t2x - 0.5 * t1x),
+                               P0.y + h * kk * V0.y + h * h * (t2y - 0.5 * t1y));
+    }
+    c1x = __shfl_sync(0xffffffffu, t1x, 31); c1y = __shfl_sync(0xffffffffu, t1y, 31);
+    c2x = __shfl_sync(0xffffffffu, t2x, 31); c2y = __shfl_sync(0xffffffffu, t2y, 31);
+  }
+}
+
+// ---------------------------------------------------------------------------------- linearize
+// CTA = (scenario b, tile of KT time steps, chunk of pair indices).  The positions of
+// all agents for the tile are staged in shared memory ([kk][i] double2); threads then
+// stream over rows p (pair index, the reference's i<j lexicographic order) writing
+// eta (double2) and the bound coalesced, and reduce min distance / first violation
+// with warp shuffles before one atomic per CTA.
+constexpr int LIN_THREADS = 256;
+
+__device__ __forceinline__ void pair_from_index(long long p, int N, int& i, int& j) {
+  // p = i (2N - i - 1)/2 + (j - i - 1)
+  const double t = 2.0 * N - 1.0;
+  int ii = (int)floor((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
+  if (ii < 0) ii = 0;
+  while ((long long)ii * (2 * N - ii - 1) / 2 > p) --ii;
+  while ((long long)(ii + 1) * (2 * N - ii - 2) / 2 <= p) ++ii;
+  i = ii;
+  j = (int)(p - (long long)ii * (2 * N - ii - 1) / 2) + ii + 1;
+}
+
+__global__ void __launch_bounds__(LIN_THREADS)
+scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int nchunks, double R, double thr,
+                     double2* __restrict__ eta, double* __restrict__ bound,
+                     unsigned long long* __restrict__ minsep_bits, unsigned long long* __restrict__ first_row) {
+  extern __shared__ double2 sp[];                       // [KT][N]
+  const int b = blockIdx.z, kt = blockIdx.y, chunk = blockIdx.x;
+  const int k0 = kt * KT, kn = min(KT, K - k0);
+  const long long P = (long long)N * (N - 1) / 2;
+  const double2* src = pos + (size_t)b * N * K;
+  for (int e = threadIdx.x; e < N * kn; e += blockDim.x) {
+    const int i = e / kn, kk = e - i * kn;              // kn contiguous double2 per agent
+    sp[kk * N + i] = src[(size_t)i * K + k0 + kk];
+  }
+  __syncthreads();
+  const long long per = (P + nchunks - 1) / nchunks;
+  const long long pa = (long long)chunk * per, pb = min(P, pa + per);
+  double mn = INFINITY;
+  unsigned long long fr = ~0ull;
+  for (int kk = 0; kk < kn; ++kk) {
+    const int k = k0 + kk;
+    const double2* row = sp + kk * N;
+    const size_t obase = ((size_t)b * K + k) * (size_t)P;
+    for (long long p = pa + threadIdx.x; p < pb; p += blockDim.x) {
+      int i, j;
+      pair_from_index(p, N, i, j);
+      const double2 a = row[i], c = row[j];
+      const double dx = a.x - c.x, dy = a.y - c.y;
+      double dist = hypot(dx, dy);                      // np.hypot, scp.py:501
+      const double dchk = sqrt(dx * dx + dy * dy);      // np.linalg.norm, scp.py:609
+      mn = fmin(mn, dchk);
+      if (dchk < thr) { unsigned long long r = (unsigned long long)k * (unsigned long long)P + (unsigned long long)p; fr = r < fr ? r : fr; }
+      if (eta) {
+        double ex, ey;
+        if (dist < 1e-6) { ex = 1.0; ey = 0.0; dist = 1.0; }   // deterministic stand-in for scp.py:503-507
+        else { ex = dx / dist; ey = dy / dist; }
+        eta[obase + p] = make_double2(ex, ey);
+        bound[obase + p] = R + ((ex * dx + ey * dy) - dist);   // scp.py:547-549 without the p0/v0 shift (T3)
+      }
+    }
+  }
+  // warp shuffle reduction, then one atomic per warp (positive doubles order like their bit patterns)
+  unsigned long long mb = (unsigned long long)__double_as_longlong(mn);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, mb, d);
+    mb = o < mb ? o : mb;
+    unsigned long long f = __shfl_xor_sync(0xffffffffu, fr, d);
+    fr = f < fr ? f : fr;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(minsep_bits + b, mb);
+    if (fr != ~0ull) atomicMin(first_row + b, fr);
+  }
+}
+
+__global__ void scp_linearize_init_kernel(unsigned long long* minsep_bits, unsigned long long* first_row, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { minsep_bits[b] = (unsigned long long)__double_as_longlong(INFINITY); first_row[b] = ~0ull; }
+}
+
+__global__ void scp_linearize_finish_kernel(const unsigned long long* minsep_bits, const unsigned long long* first_row,
+                                            int B, int N, double* minsep, int32_t* first) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (minsep) minsep[b] = __longlong_as_double((long long)minsep_bits[b]);
+  if (first) {
+    const unsigned long long P = (unsigned long long)N * (N - 1) / 2;
+    if (first_row[b] == ~0ull || P == 0) { first[3 * b] = first[3 * b + 1] = first[3 * b + 2] = -1; }
+    else {
+      int i, j;
+      pair_from_index((long long)(first_row[b] % P), N, i, j);
+      first[3 * b] = (int)(first_row[b] / P); first[3 * b + 1] = i; first[3 * b + 2] = j;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int scp_b200_abi_version(void) { return SCP_B200_ABI_VERSION; }
+size_t scp_b200_sizeof_problem(void) { return sizeof(scp_b200_problem); }
+size_t scp_b200_sizeof_record(void) { return sizeof(scp_b200_record); }
+
+const char* scp_b200_last_error(void) { return g_err.c_str(); }
+
+void scp_b200_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon, double time_step,
+                              double min_distance) {
+  scp_fill_default_problem(prob, n_agents, time_horizon, time_step, min_distance);
+}
+
+size_t scp_b200_tables_bytes(const scp_b200_problem* prob) {
+  return scp::tables_doubles(prob->n_steps) * sizeof(double);
+}
+
+int scp_b200_build_tables(const scp_b200_problem* prob, void* d_tables, void* stream) {
+  if (int rc = validate(prob)) return rc;
+  scp::HostTables t = scp::build_host_tables(*prob);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaMemcpyAsync(d_tables, t.blob.data(), t.blob.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));   // t.blob is pageable and dies with this frame
+  return 0;
+}
+
+size_t scp_b200_workspace_bytes(const scp_b200_problem* prob, int slots) {
+  scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
+  return slot_bytes(L) * (size_t)slots + 256;
+}
+
+int scp_b200_default_slots(const scp_b200_problem* prob) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
+  const size_t smem = SMEM_BASE + nmat_smem_bytes(prob->n_steps);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;                        // 4 x 512 threads = the SM's 2048
+  size_t slots = (size_t)sms * per_sm;
+  const size_t budget = (size_t)48 << 30;            // keep scratch well inside 180 GB
+  while (slots > 1 && slot_bytes(L) * slots > budget) slots /= 2;
+  return (int)slots;
+}
+
+int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0, const double* d_v0,
+                         const double* d_pf, const double* d_vf, const void* d_tables, void* d_workspace,
+                         size_t workspace_bytes, int slots, double* d_acc, double* d_pos, double* d_vel,
+                         scp_b200_record* d_records, void* stream) {
+  if (int rc = validate(prob)) return rc;
+  if (B <= 0) return 0;
+  if (slots < 1) return fail(1, "slots must be >= 1");
+  scp::Params g;
+  g.pb = *prob;
+  g.L = scp::make_layout(prob->n_agents, prob->n_steps);
+  const int K = prob->n_steps;
+  const double* tb = (const double*)d_tables;
+  g.tb.B1 = tb; g.tb.B2 = tb + (size_t)K * K; g.tb.rj = tb + 2 * (size_t)K * K;
+  g.tb.ra = g.tb.rj + K; g.tb.rv = g.tb.ra + K; g.tb.rp = g.tb.rv + K; g.tb.rc = g.tb.rp + K;
+  const size_t need = slot_bytes(g.L) * (size_t)slots + 256;
+  if (workspace_bytes < need) return fail(2, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)d_workspace;
+  unsigned int* counter = (unsigned int*)base;
+  double* ws_d = (double*)(base + 256);
+  int* ws_i = (int*)(base + 256 + g.L.n_double * sizeof(double) * (size_t)slots);
+  CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
+  const size_t nm = nmat_smem_bytes(K);
+  const size_t smem = SMEM_BASE + nm;
+  CUDA_OK(cudaFuncSetAttribute(scp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = B < slots ? B : slots;
+  scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
+                                                        d_vel, d_records, counter, nm ? 1 : 0);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+std::mutex g_cache_mu;
+struct HostCache {      // device buffers reused across scp_b200_solve_batch_host calls
+  int device = -1;
+  void* tables = nullptr; size_t tables_bytes = 0; scp_b200_problem tables_for{};
+  void* ws = nullptr; size_t ws_bytes = 0;
+  void* io = nullptr; size_t io_bytes = 0;
+  cudaStream_t stream = nullptr;
+} g_cache;
+}  // namespace
+
+int scp_b200_solve_batch_host(const scp_b200_problem* prob, int B, const double* h_p0, const double* h_v0,
+                              const double* h_pf, const double* h_vf, double* h_acc, double* h_pos,
+                              double* h_vel, scp_b200_record* h_records, int device) {
+  if (int rc = validate(prob)) return rc;
+  if (B <= 0) return 0;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  CUDA_OK(cudaSetDevice(device));
+  HostCache& hc = g_cache;
+  if (hc.device != device) {
+    hc = HostCache{};   // buffers of another device are simply dropped (process lifetime)
+    hc.device = device;
+    CUDA_OK(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
+  }
+  const int N = prob->n_agents, K = prob->n_steps;
+  const size_t tb = scp_b200_tables_bytes(prob);
+  if (tb > hc.tables_bytes) { if (hc.tables) cudaFree(hc.tables); CUDA_OK(cudaMalloc(&hc.tables, tb)); hc.tables_bytes = tb; memset(&hc.tables_for, 0, sizeof(hc.tables_for)); }
+  if (memcmp(&hc.tables_for, prob, sizeof(*prob)) != 0) {
+    if (int rc = scp_b200_build_tables(prob, hc.tables, hc.stream)) return rc;
+    hc.tables_for = *prob;
+  }
+  int slots = scp_b200_default_slots(prob);
+  if (slots > B) slots = B;
+  const size_t wb = scp_b200_workspace_bytes(prob, slots);
+  if (wb > hc.ws_bytes) { if (hc.ws) cudaFree(hc.ws); CUDA_OK(cudaMalloc(&hc.ws, wb)); hc.ws_bytes = wb; }
+  const size_t n2 = (size_t)B * N * 2 * sizeof(double), n3 = (size_t)B * N * K * 2 * sizeof(double);
+  const size_t nr = (size_t)B * sizeof(scp_b200_record);
+  const size_t iob = 4 * n2 + 3 * n3 + nr + 1024;
+  if (iob > hc.io_bytes) { if (hc.io) cudaFree(hc.io); CUDA_OK(cudaMalloc(&hc.io, iob)); hc.io_bytes = iob; }
+  char* io = (char*)hc.io;
+  double *d_p0 = (double*)io, *d_v0 = (double*)(io + n2), *d_pf = (double*)(io + 2 * n2), *d_vf = (double*)(io + 3 * n2);
+  double *d_acc = (double*)(io + 4 * n2), *d_pos = (double*)(io + 4 * n2 + n3), *d_vel = (double*)(io + 4 * n2 + 2 * n3);
+  scp_b200_record* d_rec = (scp_b200_record*)(io + 4 * n2 + 3 * n3);
+  cudaStream_t st = hc.stream;
+  CUDA_OK(cudaMemcpyAsync(d_p0, h_p0, n2, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_v0, h_v0, n2, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_pf, h_pf, n2, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(d_vf, h_vf, n2, cudaMemcpyHostToDevice, st));
+  if (int rc = scp_b200_solve_batch(prob, B, d_p0, d_v0, d_pf, d_vf, hc.tables, hc.ws, hc.ws_bytes, slots, d_acc,
+                                    d_pos, d_vel, d_rec, st))
+    return rc;
+  if (h_acc) CUDA_OK(cudaMemcpyAsync(h_acc, d_acc, n3, cudaMemcpyDeviceToHost, st));
+  if (h_pos) CUDA_OK(cudaMemcpyAsync(h_pos, d_pos, n3, cudaMemcpyDeviceToHost, st));
+  if (h_vel) CUDA_OK(cudaMemcpyAsync(h_vel, d_vel, n3, cudaMemcpyDeviceToHost, st));
+  if (h_records) CUDA_OK(cudaMemcpyAsync(h_records, d_rec, nr, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int scp_b200_reconstruct(const double* d_acc, const double* d_p0, const double* d_v0, int B, int N, int K,
+                         double h, double* d_pos, double* d_vel, void* stream) {
+  if (B <= 0 || N <= 0) return 0;
+  if (K < 1) return fail(1, "n_steps must be >= 1");
+  const long long BN = (long long)B * N;
+  const int wpb = 256 / 32;
+  const long long blocks = (BN + wpb - 1) / wpb;
+  if (blocks > 0x7fffffffLL) return fail(1, "too many agents for one launch");
+  scp_reconstruct_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const double2*)d_acc, (const double2*)d_p0, (const double2*)d_v0, (int)BN, K, h, (double2*)d_pos,
+      (double2*)d_vel);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, double feas_margin, double* d_eta,
+                       double* d_bound, double* d_minsep, int32_t* d_first, void* stream) {
+  if (B <= 0) return 0;
+  if (N < 1 || K < 1) return fail(1, "bad sizes");
+  if ((d_eta == nullptr) != (d_bound == nullptr)) return fail(1, "d_eta and d_bound must both be given or both NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch for the two 64-bit reductions, allocated stream-ordered
+  unsigned long long* red = nullptr;
+  CUDA_OK(cudaMallocAsync((void**)&red, 2 * (size_t)B * sizeof(unsigned long long), st));
+  scp_linearize_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(red, red + B, B);
+  if (N >= 2) {
+    int KT = 8;
+    while (KT > 1 && (size_t)KT * N * sizeof(double2) > 200 * 1024) KT >>= 1;
+    if ((size_t)KT * N * sizeof(double2) > 200 * 1024) { cudaFreeAsync(red, st); return fail(1, "n_agents too large for the position tile"); }
+    const int ktiles = (K + KT - 1) / KT;
+    const long long P = (long long)N * (N - 1) / 2;
+    long long want = (4LL * 148 + (long long)B * ktiles - 1) / ((long long)B * ktiles);   // >= 4 CTAs per SM in total
+    long long maxc = (P + 2047) / 2048;
+    int nchunks = (int)(want < 1 ? 1 : (want > maxc ? maxc : want));
+    if (nchunks < 1) nchunks = 1;
+    const size_t smem = (size_t)KT * N * sizeof(double2);
+    CUDA_OK(cudaFuncSetAttribute(scp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nchunks, ktiles, B);
+    scp_linearize_kernel<<<grid, LIN_THREADS, smem, st>>>((const double2*)d_pos, N, K, KT, nchunks, R,
+                                                          R - feas_margin, (double2*)d_eta, d_bound, red, red + B);
+  }
+  scp_linearize_finish_kernel<<<(B + 255) / 256, 256, 0, st>>>(red, red + B, B, N, d_minsep, d_first);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(red, st);
+  CUDA_OK(e);
+  return 0;
+}
+
+}  // extern "C"

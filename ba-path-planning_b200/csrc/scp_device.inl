@@ -1,0 +1,843 @@
+// scp_device.inl -- the SCP solver for one scenario, executed by one CTA.
+//
+// Written "phase style": every SCP_PHASE block is a data-parallel loop over the
+// CTA's threads and phases are separated by SCP_SYNC.  With SCP_EMU defined the
+// same source compiles as plain C++ where a phase is a sequential loop over
+// thread ids (tests/ only -- used to debug the kernel logic without a GPU; the
+// product never loads it).
+//
+// What it replaces in the reference (src/path_planning/solvers/scp.py):
+//   setup_scenario      _precompute_constraint_matrices bounds      :205-257
+//   factor_operator     OSQP setup / KKT factorisation              :360, :442
+//   admm_run            problem.solve()                             :362, :445
+//   forward_rows        _accelerations_to_positions_velocities      :559-595
+//   build_candidates    _add_collision_constraints (matrix free)    :453-557
+//   gate_and_minsep     _fast_check_avoidance_constraints           :597-615
+//   solve_scenario      generate_trajectories                       :131-180
+//
+// Decision vector: a[i][k][axis] (scp.py:15-26); internally one "agent-axis"
+// q = 2 i + axis owns a K-vector stored contiguously: x[q*K + k].
+//
+// QP solver: ADMM on  min sum a^2  s.t.  A a = z, z in C, with
+//   * the 2 terminal equalities per agent-axis handled exactly inside the
+//     x-update (affine constraint of f),
+//   * box rows (jerk, acc, vel, pos) in the (v = z + y/rho) form: one double of
+//     state per row, z = clip(v), y = rho (v - z),
+//   * collision rows eta.(p_i - p_j) >= bound split on per-agent copies of the
+//     two positions; the copy multipliers stay on span{(eta,-eta)} so one scalar
+//     lam >= 0 per row is the whole state, and the x-update operator is one
+//     K x K matrix shared by every agent-axis of the scenario:
+//        M = (2+sigma) I + rho (D'RjD + Ra + V'RvV + S'RpS) + rho c S'RcS
+//     (c = copies = max candidate rows per (agent, step)).
+// Only rows whose linearisation-point distance is below R + margin are carried
+// ("candidates"); after convergence every dropped row is verified and the
+// candidate set enlarged if one is violated, so the result is the minimiser of
+// the full QP.  DESIGN.md derives all of this.
+
+#ifndef SCP_DEVICE_INL
+#define SCP_DEVICE_INL
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/scp_b200.h"
+
+#ifdef SCP_EMU
+#define SCP_DEV inline
+#define SCP_PHASE(c) for (int tid = 0; tid < (c).nthreads; ++tid)
+#define SCP_SYNC(c) ((void)0)
+#define SCP_FMAX(a, b) ((a) > (b) ? (a) : (b))
+#define SCP_FMIN(a, b) ((a) < (b) ? (a) : (b))
+#else
+#define SCP_DEV __device__ __forceinline__
+#define SCP_PHASE(c) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
+#define SCP_SYNC(c) __syncthreads()
+#define SCP_FMAX(a, b) fmax(a, b)
+#define SCP_FMIN(a, b) fmin(a, b)
+#endif
+
+namespace scp {
+
+constexpr int CH = 8;           // scan chunk length
+constexpr int RED = 1024;       // reduction scratch entries (>= max threads)
+
+struct Tables {                 // constant per (K, h, weights); unit rho
+  const double* B1;             // K*K  D'RjD + Ra + V'RvV + S'RpS
+  const double* B2;             // K*K  S'RcS (one copy)
+  const double* rj;             // K
+  const double* ra;             // K
+  const double* rv;             // K
+  const double* rp;             // K
+  const double* rc;             // K
+};
+
+// Offsets (in doubles / ints) of the per-slot scratch.
+struct Layout {
+  size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
+  size_t c_eta, c_bound, lam, scr, red, n_double;
+  size_t cnt, coff, c_j, flags, n_int;
+  size_t cap;
+};
+
+inline
+#ifndef SCP_EMU
+__host__ __device__
+#endif
+Layout make_layout(int N, int K) {
+  Layout L;
+  size_t Q = 2 * (size_t)N, QK = Q * K, o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 1) & ~(size_t)1; return r; };
+  L.Minv = take((size_t)K * K);
+  L.N0 = take(2 * (size_t)K);
+  L.Qm = take(2 * (size_t)K);
+  L.x = take(QK); L.xprev = take(QK); L.rhs = take(QK);
+  L.vj = take(QK); L.va = take(QK); L.vv = take(QK); L.vp = take(QK);
+  L.posrow = take(QK); L.velrow = take(QK);
+  L.P = take(QK); L.Pbar = take(QK); L.F = take(QK); L.FY = take(QK);
+  L.off = take(QK); L.deq = take(2 * Q); L.mu = take(2 * Q);
+  L.cap = (size_t)N * (size_t)K * (size_t)(N > 1 ? N - 1 : 1);
+  L.c_eta = take(2 * L.cap); L.c_bound = take(L.cap); L.lam = take((size_t)N * N * K);
+  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 8);
+  L.red = take(4 * RED);
+  L.n_double = o;
+  size_t p = 0;
+  auto takei = [&](size_t n) { size_t r = p; p += (n + 3) & ~(size_t)3; return r; };
+  L.cnt = takei((size_t)N * K + 1); L.coff = takei((size_t)N * K + 1); L.c_j = takei(L.cap); L.flags = takei(((size_t)N * N * K + 3) / 4);
+  L.n_int = p;
+  return L;
+}
+
+struct Params {                 // one per launch (kernel parameter / constant bank)
+  scp_b200_problem pb;
+  Tables tb;
+  Layout L;
+};
+
+struct Ctx {
+  int nthreads;
+  int N, K, Q;                  // Q = 2N agent-axes
+  const Params* g;
+  double* wd;                   // slot scratch (doubles)
+  int* wi;                      // slot scratch (ints)
+  double* sm;                   // shared scratch: [0,4*RED) reductions, then optional Nmat copy
+  const double* nmat;           // where P2 reads the operator from (shared or global)
+  int nmat_in_smem;
+  // per scenario
+  const double *p0, *v0, *pf, *vf;
+  double *acc, *pos, *vel;
+  scp_b200_record* rec;
+  // block-uniform solver state
+  double rho;
+  int copies;
+  int ncand;
+};
+
+// ------------------------------------------------------------------ reductions
+// Phase-style block reductions over a value every thread contributes.
+// kind 0: max, 1: sum.  Result returned to all threads.
+#define SCP_REDUCE_BEGIN(c, slot) double* _red = (c).sm + (slot) * RED
+SCP_DEV double reduce_finish(Ctx& c, int slot, int kind) {
+  double* red = c.sm + slot * RED;
+  SCP_PHASE(c) {
+    if (tid < 32) {
+      double a = kind ? 0.0 : -INFINITY;
+      for (int e = tid; e < c.nthreads; e += 32) a = kind ? a + red[e] : SCP_FMAX(a, red[e]);
+      red[RED - 32 + tid] = a;   // nthreads <= RED - 32
+    }
+  }
+  SCP_SYNC(c);
+  double r = kind ? 0.0 : -INFINITY;
+  for (int e = 0; e < 32; ++e) r = kind ? r + red[RED - 32 + e] : SCP_FMAX(r, red[RED - 32 + e]);
+  SCP_SYNC(c);
+  return r;
+}
+
+SCP_DEV double clampd(double v, double lo, double hi) { return SCP_FMIN(SCP_FMAX(v, lo), hi); }
+
+// ------------------------------------------------------------------ scenario setup
+// off[q][k] = p0 + h (k+1) v0 : constant part of position state k+1 (scp.py:246-247)
+// deq[q] = (vf - v0, pf - off[K-1])  terminal equalities (scp.py:223-224, 256-257)
+SCP_DEV void setup_scenario(Ctx& c) {
+  const int K = c.K;
+  double* off = c.wd + c.g->L.off;
+  double* deq = c.wd + c.g->L.deq;
+  double* x = c.wd + c.g->L.x;
+  const double h = c.g->pb.time_step;
+  SCP_PHASE(c) {
+    for (int e = tid; e < c.Q * K; e += c.nthreads) {
+      int q = e / K, k = e - q * K;
+      off[e] = c.p0[q] + h * (double)(k + 1) * c.v0[q];
+      x[e] = 0.0;
+    }
+    for (int q = tid; q < c.Q; q += c.nthreads) {
+      deq[2 * q + 0] = c.vf[q] - c.v0[q];
+      deq[2 * q + 1] = c.pf[q] - (c.p0[q] + h * (double)K * c.v0[q]);
+    }
+  }
+  SCP_SYNC(c);
+}
+
+// ------------------------------------------------------------------ operator
+// Minv <- inverse of M(rho, copies) by in-place Gauss-Jordan (SPD, no pivoting),
+// then the equality-constrained solution operator
+//   x = Nmat r + N0 d,   mu = Qm r - G d,   Nmat = Minv - Minv C'(C Minv C')^-1 C Minv
+// C = [h 1' ; S[K-1,:]] (terminal velocity / position rows).
+SCP_DEV void factor_operator(Ctx& c) {
+  const int K = c.K;
+  double* M = c.wd + c.g->L.Minv;
+  double* N0 = c.wd + c.g->L.N0;
+  double* Qm = c.wd + c.g->L.Qm;
+  double* colb = c.sm;             // K  (K <= RED assumed for the scratch; checked on host)
+  double* rowb = c.sm + RED;       // K
+  double* mc = c.sm + 2 * RED;     // 2K : Minv C'
+  const double rho = c.rho, sig = c.g->pb.sigma, cp = (double)c.copies;
+  const double h = c.g->pb.time_step;
+  SCP_PHASE(c) {
+    for (int e = tid; e < K * K; e += c.nthreads) {
+      int r = e / K, cc = e - r * K;
+      M[e] = rho * (c.g->tb.B1[e] + cp * c.g->tb.B2[e]) + (r == cc ? 2.0 + sig : 0.0);
+    }
+  }
+  SCP_SYNC(c);
+  for (int p = 0; p < K; ++p) {
+    SCP_PHASE(c) {
+      for (int e = tid; e < K; e += c.nthreads) { colb[e] = M[e * K + p]; rowb[e] = M[p * K + e]; }
+    }
+    SCP_SYNC(c);
+    const double ip = 1.0 / colb[p];
+    SCP_PHASE(c) {
+      for (int e = tid; e < K * K; e += c.nthreads) {
+        int r = e / K, cc = e - r * K;
+        double v;
+        if (r == p) v = (cc == p) ? ip : rowb[cc] * ip;
+        else if (cc == p) v = -colb[r] * ip;
+        else v = M[e] - colb[r] * rowb[cc] * ip;
+        M[e] = v;
+      }
+    }
+    SCP_SYNC(c);
+  }
+  // mc[k][e] = sum_j Minv[k][j] C[e][j]
+  SCP_PHASE(c) {
+    for (int k = tid; k < K; k += c.nthreads) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int j = 0; j < K; ++j) {
+        double m = M[k * K + j];
+        a0 += m * h;
+        a1 += m * (h * h * ((double)(K - 1 - j) + 0.5));
+      }
+      mc[2 * k] = a0; mc[2 * k + 1] = a1;
+    }
+  }
+  SCP_SYNC(c);
+  double h00 = 0, h01 = 0, h11 = 0;   // H = C mc (2x2, symmetric); every thread computes it
+  for (int k = 0; k < K; ++k) {
+    double cv = h, cpk = h * h * ((double)(K - 1 - k) + 0.5);
+    h00 += cv * mc[2 * k]; h01 += cv * mc[2 * k + 1]; h11 += cpk * mc[2 * k + 1];
+  }
+  const double det = h00 * h11 - h01 * h01;
+  const double g00 = h11 / det, g01 = -h01 / det, g11 = h00 / det;
+  SCP_PHASE(c) {
+    for (int k = tid; k < K; k += c.nthreads) {
+      double n0 = mc[2 * k] * g00 + mc[2 * k + 1] * g01;
+      double n1 = mc[2 * k] * g01 + mc[2 * k + 1] * g11;
+      N0[2 * k] = n0; N0[2 * k + 1] = n1;          // N0 = mc G
+      Qm[k] = n0; Qm[K + k] = n1;                  // Qm = G mc' (G symmetric)
+    }
+    if (tid == 0) { c.sm[3 * RED + 0] = g00; c.sm[3 * RED + 1] = g01; c.sm[3 * RED + 2] = g11; }
+  }
+  SCP_SYNC(c);
+  SCP_PHASE(c) {
+    for (int e = tid; e < K * K; e += c.nthreads) {
+      int r = e / K, cc = e - r * K;
+      M[e] -= mc[2 * r] * Qm[cc] + mc[2 * r + 1] * Qm[K + cc];
+    }
+  }
+  SCP_SYNC(c);
+  if (c.nmat_in_smem) {
+    double* dst = c.sm + 4 * RED;
+    SCP_PHASE(c) { for (int e = tid; e < K * K; e += c.nthreads) dst[e] = M[e]; }
+    SCP_SYNC(c);
+    c.nmat = dst;
+  } else {
+    c.nmat = M;
+  }
+}
+
+// ------------------------------------------------------------------ forward rows
+// rows of A x for every agent-axis: jerk (D x), vel (h cumsum), pos (h^2 (cumsum2 - cumsum/2)).
+// mode 0: initialise v := A x (y = 0)            (OSQP warm start with x only, scp.py:443)
+// mode 1: ADMM update v := A x + (v - clip(v))
+// Also writes posrow/velrow and the positions P[q][k], k = 1..K-1 (P[q][0] = p0).
+SCP_DEV void forward_rows(Ctx& c, int mode) {
+  const int K = c.K, nch = (K + CH - 1) / CH;
+  const double h = c.g->pb.time_step, ih = 1.0 / h;
+  double* x = c.wd + c.g->L.x;
+  double* s1 = c.wd + c.g->L.scr;            // chunk totals
+  double* s2 = s1 + (size_t)c.Q * nch;
+  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+  double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *P = c.wd + c.g->L.P, *off = c.wd + c.g->L.off;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  SCP_PHASE(c) {
+    for (int t = tid; t < c.Q * nch; t += c.nthreads) {
+      int q = t / nch, ch = t - q * nch;
+      int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
+      double a1 = 0, a2 = 0;
+      for (int k = k0; k < k1; ++k) { a1 += x[q * K + k]; a2 += a1; }
+      s1[t] = a1; s2[t] = a2;
+    }
+  }
+  SCP_SYNC(c);
+  SCP_PHASE(c) {
+    for (int t = tid; t < c.Q * nch; t += c.nthreads) {
+      int q = t / nch, ch = t - q * nch;
+      int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
+      double c1 = 0, c2 = 0;
+      for (int cc = 0; cc < ch; ++cc) { c2 += s2[q * nch + cc] + (double)CH * c1; c1 += s1[q * nch + cc]; }
+      const double v0q = c.v0[q];
+      const double lv = -vl - v0q, uv = vl - v0q;
+      const int ax = q & 1;
+      for (int k = k0; k < k1; ++k) {
+        const int e = q * K + k;
+        const double xk = x[e];
+        c1 += xk; c2 += c1;
+        const double rv_ = h * c1, rp_ = h * h * (c2 - 0.5 * c1);
+        velrow[e] = rv_; posrow[e] = rp_;
+        if (k + 1 < K) P[q * K + k + 1] = off[e] + rp_;
+        if (mode == 0) {
+          va[e] = xk;
+          if (k < K - 1) { vj[e] = (x[e + 1] - xk) * ih; vv[e] = rv_; vp[e] = rp_; }
+        } else {
+          double v = va[e]; va[e] = xk + (v - clampd(v, -al, al));
+          if (k < K - 1) {
+            v = vj[e]; vj[e] = (x[e + 1] - xk) * ih + (v - clampd(v, -jl, jl));
+            v = vv[e]; vv[e] = rv_ + (v - clampd(v, lv, uv));
+            v = vp[e]; vp[e] = rp_ + (v - clampd(v, lo[ax] - off[e], hi[ax] - off[e]));
+          }
+        }
+      }
+      if (ch == 0) P[q * K] = c.p0[q];
+    }
+  }
+  SCP_SYNC(c);
+}
+
+// ------------------------------------------------------------------ transpose scans
+// out[m] = base(m) + (D'wj)[m] + wa[m] + h sum_{k>=m} wv[k] + h^2 sum_{k>=m} (k-m+1/2) wp[k]
+// mode 0 (rhs of the x-update):  w = rho r (2 clip(v) - v); wp += rho c rc posrow + F; base = sigma x
+// mode 1 (dual residual):        w = rho r (v - clip(v)) = y; wp -= FY; base = 2 x + C'mu
+//   in mode 1 the result is written to rhs and max|.| terms are left to the caller.
+SCP_DEV void transpose_rows(Ctx& c, int mode) {
+  const int K = c.K, nch = (K + CH - 1) / CH;
+  const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho;
+  double* x = c.wd + c.g->L.x;
+  double* out = c.wd + c.g->L.rhs;
+  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+  double *posrow = c.wd + c.g->L.posrow, *off = c.wd + c.g->L.off, *mu = c.wd + c.g->L.mu;
+  double* Fm = c.wd + (mode == 0 ? c.g->L.F : c.g->L.FY);
+  double* t1 = c.wd + c.g->L.scr;          // chunk totals
+  double* t2 = t1 + (size_t)c.Q * nch;
+  double* t3 = t2 + (size_t)c.Q * nch;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  const double cpr = (double)c.copies * rho;
+  const double sig = c.g->pb.sigma;
+  for (int pass = 0; pass < 2; ++pass) {
+    SCP_PHASE(c) {
+      for (int t = tid; t < c.Q * nch; t += c.nthreads) {
+        int q = t / nch, ch = t - q * nch;
+        int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
+        const double v0q = c.v0[q];
+        const double lv = -vl - v0q, uv = vl - v0q;
+        const int ax = q & 1;
+        double r1v = 0, r1p = 0, r2p = 0;
+        if (pass == 1) {
+          for (int cc = nch - 1; cc > ch; --cc) {
+            int len = (cc * CH + CH < K ? CH : K - cc * CH);
+            r2p += t3[q * nch + cc] + (double)len * r1p;
+            r1p += t2[q * nch + cc];
+            r1v += t1[q * nch + cc];
+          }
+        }
+        for (int k = k1 - 1; k >= k0; --k) {
+          const int e = q * K + k;
+          double wv = 0, wp = 0;
+          if (k < K - 1) {
+            double v = vv[e], z = clampd(v, lv, uv);
+            wv = rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : v - z);
+            v = vp[e]; z = clampd(v, lo[ax] - off[e], hi[ax] - off[e]);
+            wp = rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : v - z);
+            // force on position state k+1 <-> row k
+            if (mode == 0) wp += cpr * c.g->tb.rc[k] * posrow[e] + Fm[q * K + k + 1];
+            else wp -= Fm[q * K + k + 1];
+          }
+          r1v += wv; r1p += wp; r2p += r1p;
+          if (pass == 1) {
+            double v = va[e], z = clampd(v, -al, al);
+            double o = rho * c.g->tb.ra[k] * (mode == 0 ? 2 * z - v : v - z);
+            double wj0 = 0, wj1 = 0;   // wj[k-1], wj[k]
+            if (k >= 1) { v = vj[e - 1]; z = clampd(v, -jl, jl); wj0 = rho * c.g->tb.rj[k - 1] * (mode == 0 ? 2 * z - v : v - z); }
+            if (k < K - 1) { v = vj[e]; z = clampd(v, -jl, jl); wj1 = rho * c.g->tb.rj[k] * (mode == 0 ? 2 * z - v : v - z); }
+            o += (wj0 - wj1) * ih + h * r1v + h * h * (r2p - 0.5 * r1p);
+            if (mode == 0) o += sig * x[e];
+            else o += 2.0 * x[e] + h * mu[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * mu[2 * q + 1];
+            out[e] = o;
+          }
+        }
+        if (pass == 0) { t1[t] = r1v; t2[t] = r1p; t3[t] = r2p; }
+      }
+    }
+    SCP_SYNC(c);
+  }
+}
+
+// ------------------------------------------------------------------ x-update
+SCP_DEV void x_update(Ctx& c, int want_mu) {
+  const int K = c.K;
+  double* x = c.wd + c.g->L.x;
+  const double* rhs = c.wd + c.g->L.rhs;
+  const double* N0 = c.wd + c.g->L.N0;
+  const double* Qm = c.wd + c.g->L.Qm;
+  const double* deq = c.wd + c.g->L.deq;
+  double* mu = c.wd + c.g->L.mu;
+  const double* Nm = c.nmat;
+  SCP_PHASE(c) {
+    for (int e = tid; e < c.Q * K; e += c.nthreads) {
+      int q = e / K, k = e - q * K;
+      const double* r = rhs + (size_t)q * K;
+      double a = N0[2 * k] * deq[2 * q] + N0[2 * k + 1] * deq[2 * q + 1];
+      for (int j = 0; j < K; ++j) a += Nm[j * K + k] * r[j];   // Nmat symmetric: column read is coalesced
+      x[e] = a;
+    }
+    if (want_mu) {
+      const double g00 = c.sm[3 * RED + 0], g01 = c.sm[3 * RED + 1], g11 = c.sm[3 * RED + 2];
+      for (int t = tid; t < 2 * c.Q; t += c.nthreads) {
+        int q = t >> 1, ee = t & 1;
+        const double* r = rhs + (size_t)q * K;
+        double a = 0;
+        for (int j = 0; j < K; ++j) a += Qm[ee * K + j] * r[j];
+        double gd = ee == 0 ? g00 * deq[2 * q] + g01 * deq[2 * q + 1] : g01 * deq[2 * q] + g11 * deq[2 * q + 1];
+        mu[t] = a - gd;
+      }
+    }
+  }
+  SCP_SYNC(c);
+}
+
+// ------------------------------------------------------------------ collision rows
+// One thread per (k, i), k = 1..K-1: walks its candidate rows, updates the row
+// multipliers (both owners of a row update their own copy identically) and sums
+// the force on p_i[k].  Returns (through red slot 0) max |dlam|/rho_c = primal
+// residual of the copy rows when `want_res`.
+SCP_DEV void collision_rows(Ctx& c, int want_res) {
+  const int K = c.K, N = c.N;
+  const double* P = c.wd + c.g->L.P;
+  double* F = c.wd + c.g->L.F;
+  double* FY = c.wd + c.g->L.FY;
+  const int* coff = c.wi + c.g->L.coff;
+  const int* cj = c.wi + c.g->L.c_j;
+  const double* ceta = c.wd + c.g->L.c_eta;
+  const double* cb = c.wd + c.g->L.c_bound;
+  double* lam = c.wd + c.g->L.lam;        // dense [k][i][j]; the two owners keep identical copies
+  double* red = c.sm;
+  const double rho = c.rho;
+  SCP_PHASE(c) {
+    double worst = 0.0;
+    for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+      int k = 1 + t / N, i = t - (k - 1) * N;
+      const double pix = P[(2 * i) * K + k], piy = P[(2 * i + 1) * K + k];
+      const double rc = rho * c.g->tb.rc[k - 1];
+      double fx = 0, fy = 0, yx = 0, yy = 0;
+      for (int s = coff[k * N + i]; s < coff[k * N + i + 1]; ++s) {
+        const int j = cj[s];
+        const double ex = ceta[2 * s], ey = ceta[2 * s + 1];
+        const double g = ex * (pix - P[(2 * j) * K + k]) + ey * (piy - P[(2 * j + 1) * K + k]);
+        const size_t li = ((size_t)k * N + i) * N + j;
+        const double l0 = lam[li];
+        const double l1 = SCP_FMAX(0.0, l0 + 0.5 * rc * (cb[s] - g));
+        lam[li] = l1;
+        const double f = 2.0 * l1 - l0;
+        fx += f * ex; fy += f * ey;
+        yx += l1 * ex; yy += l1 * ey;
+        worst = SCP_FMAX(worst, fabs(l1 - l0) / rc);
+      }
+      F[(2 * i) * K + k] = fx; F[(2 * i + 1) * K + k] = fy;
+      if (want_res) { FY[(2 * i) * K + k] = yx; FY[(2 * i + 1) * K + k] = yy; }
+    }
+    if (want_res) red[tid] = worst;
+  }
+  SCP_SYNC(c);
+}
+
+// Candidate rows.  flags[k][i][j] != 0 marks row (k,i,j) as carried by the ADMM.
+// mark_near_rows: start of a subproblem -- rows whose linearisation-point distance
+//   is below R + margin (and their multipliers zeroed: OSQP starts every
+//   subproblem from y = 0, scp.py:441-443).
+// build_candidates: CSR over the flagged rows, per owner (k,i): partner j, eta
+//   oriented towards the owner (scp.py:498-509), bound = R + (eta.d - dist)
+//   (scp.py:547-549).  Degenerate pairs (dist < 1e-6) get the deterministic
+//   direction (+-1, 0) and dist := 1 (the reference draws a random one, :503-507).
+// verify_rows: every row of the full QP evaluated at the current positions; a
+//   violated row that is not carried is flagged (multiplier 0) and counted.
+SCP_DEV void mark_near_rows(Ctx& c, double margin) {
+  const int K = c.K, N = c.N;
+  const double* Pb = c.wd + c.g->L.Pbar;
+  unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
+  double* lam = c.wd + c.g->L.lam;
+  double* F = c.wd + c.g->L.F;
+  const double R = c.g->pb.min_distance;
+  const double r2 = (R + margin) * (R + margin);
+  SCP_PHASE(c) {
+    for (int t = tid; t < K * N; t += c.nthreads) {
+      int k = t / N, i = t - k * N;
+      const double pix = Pb[(2 * i) * K + k], piy = Pb[(2 * i + 1) * K + k];
+      for (int j = 0; j < N; ++j) {
+        double dx = pix - Pb[(2 * j) * K + k], dy = piy - Pb[(2 * j + 1) * K + k];
+        int near = (k >= 1) && (j != i) && (dx * dx + dy * dy < r2);
+        flags[(size_t)t * N + j] = (unsigned char)near;
+        if (near) lam[(size_t)t * N + j] = 0.0;
+      }
+    }
+    for (int e = tid; e < c.Q * K; e += c.nthreads) F[e] = 0.0;
+  }
+  SCP_SYNC(c);
+}
+
+SCP_DEV void build_candidates(Ctx& c) {
+  const int K = c.K, N = c.N;
+  const double* Pb = c.wd + c.g->L.Pbar;
+  const unsigned char* flags = (const unsigned char*)(c.wi + c.g->L.flags);
+  int* cnt = c.wi + c.g->L.cnt;
+  int* coff = c.wi + c.g->L.coff;
+  int* cj = c.wi + c.g->L.c_j;
+  double* ceta = c.wd + c.g->L.c_eta;
+  double* cb = c.wd + c.g->L.c_bound;
+  const double R = c.g->pb.min_distance;
+  const int total = K * N;
+  SCP_PHASE(c) {
+    for (int t = tid; t < total; t += c.nthreads) {
+      int n = 0;
+      for (int j = 0; j < N; ++j) n += flags[(size_t)t * N + j];
+      cnt[t] = n;
+    }
+  }
+  SCP_SYNC(c);
+  // exclusive scan of cnt -> coff (two-level, phase style), max -> copies
+  const int per = (total + c.nthreads - 1) / c.nthreads;
+  int* part = (int*)(c.sm + 2 * RED);        // nthreads ints
+  int* pmax = part + RED;
+  SCP_PHASE(c) {
+    int s = 0, m = 0;
+    for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { s += cnt[e]; m = cnt[e] > m ? cnt[e] : m; }
+    part[tid] = s; pmax[tid] = m;
+  }
+  SCP_SYNC(c);
+  SCP_PHASE(c) {
+    int base = 0;
+    for (int e = 0; e < tid; ++e) base += part[e];
+    for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { coff[e] = base; base += cnt[e]; }
+    if (tid == c.nthreads - 1) coff[total] = base;
+  }
+  SCP_SYNC(c);
+  int mx = 0;
+  for (int e = 0; e < c.nthreads; ++e) mx = pmax[e] > mx ? pmax[e] : mx;
+  c.copies = mx;
+  c.ncand = coff[total];
+  SCP_SYNC(c);
+  SCP_PHASE(c) {
+    for (int t = tid; t < total; t += c.nthreads) {
+      int k = t / N, i = t - k * N;
+      if (cnt[t] == 0) continue;
+      int s = coff[t];
+      const double pix = Pb[(2 * i) * K + k], piy = Pb[(2 * i + 1) * K + k];
+      for (int j = 0; j < N; ++j) {
+        if (!flags[(size_t)t * N + j]) continue;
+        double dx = pix - Pb[(2 * j) * K + k], dy = piy - Pb[(2 * j + 1) * K + k];
+        double dist = hypot(dx, dy), ex, ey;
+        if (dist < 1e-6) { ex = i < j ? 1.0 : -1.0; ey = 0.0; cb[s] = R + (ex * dx + ey * dy - 1.0); }
+        else { ex = dx / dist; ey = dy / dist; cb[s] = R + ((ex * dx + ey * dy) - dist); }
+        cj[s] = j; ceta[2 * s] = ex; ceta[2 * s + 1] = ey;
+        ++s;
+      }
+    }
+  }
+  SCP_SYNC(c);
+}
+
+SCP_DEV int verify_rows(Ctx& c, double tol) {
+  const int K = c.K, N = c.N;
+  const double* Pb = c.wd + c.g->L.Pbar;
+  const double* P = c.wd + c.g->L.P;
+  unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
+  double* lam = c.wd + c.g->L.lam;
+  const double R = c.g->pb.min_distance;
+  double* red = c.sm;
+  SCP_PHASE(c) {
+    double bad = 0.0;
+    for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+      int k = 1 + t / N, i = t - (k - 1) * N;
+      const double bx = Pb[(2 * i) * K + k], by = Pb[(2 * i + 1) * K + k];
+      const double px = P[(2 * i) * K + k], py = P[(2 * i + 1) * K + k];
+      for (int j = i + 1; j < N; ++j) {
+        const size_t fij = ((size_t)k * N + i) * N + j, fji = ((size_t)k * N + j) * N + i;
+        if (flags[fij]) continue;
+        double dx = bx - Pb[(2 * j) * K + k], dy = by - Pb[(2 * j + 1) * K + k];
+        double dist = hypot(dx, dy), ex, ey, bound;
+        if (dist < 1e-6) { ex = 1.0; ey = 0.0; bound = R + (dx - 1.0); }
+        else { ex = dx / dist; ey = dy / dist; bound = R + ((ex * dx + ey * dy) - dist); }
+        double g = ex * (px - P[(2 * j) * K + k]) + ey * (py - P[(2 * j + 1) * K + k]);
+        if (g < bound - tol) {
+          flags[fij] = 1; flags[fji] = 1; lam[fij] = 0.0; lam[fji] = 0.0;
+          bad += 1.0;
+        }
+      }
+    }
+    red[tid] = bad;
+  }
+  SCP_SYNC(c);
+  return (int)reduce_finish(c, 0, 1);
+}
+
+// _fast_check_avoidance_constraints (scp.py:597-615) on positions P (k = 0..K-1):
+// min separation and the first row in scan order (k-major, i<j) below R - margin.
+SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, double* first_dist) {
+  const int K = c.K, N = c.N;
+  const double* P = c.wd + c.g->L.P;
+  const double thr = c.g->pb.min_distance - c.g->pb.feas_margin;
+  double* red = c.sm;            // slot 0: -min distance ; slot 1: -(first row index) ; slot 2: dist of it
+  const long long npairs = (long long)N * (N - 1) / 2;
+  SCP_PHASE(c) {
+    double mn = INFINITY, fr = INFINITY, fd = 0.0;
+    for (int t = tid; t < K * N; t += c.nthreads) {
+      int k = t / N, i = t - k * N;
+      const double px = P[(2 * i) * K + k], py = P[(2 * i + 1) * K + k];
+      for (int j = i + 1; j < N; ++j) {
+        double dx = px - P[(2 * j) * K + k], dy = py - P[(2 * j + 1) * K + k];
+        // np.linalg.norm of a 2-vector: sqrt(dx^2 + dy^2)
+        double d = sqrt(dx * dx + dy * dy);
+        mn = SCP_FMIN(mn, d);
+        if (d < thr) {
+          double row = (double)((long long)k * npairs + ((long long)i * (2 * N - i - 1)) / 2 + (j - i - 1));
+          if (row < fr) { fr = row; fd = d; }
+        }
+      }
+    }
+    red[tid] = -mn; red[RED + tid] = -fr; red[2 * RED + tid] = fd;
+  }
+  SCP_SYNC(c);
+  // first row: max of -fr, carrying its distance
+  double best = -INFINITY, bd = 0.0;
+  for (int e = 0; e < c.nthreads; ++e) if (red[RED + e] > best) { best = red[RED + e]; bd = red[2 * RED + e]; }
+  double m = reduce_finish(c, 0, 0);
+  *minsep = -m;
+  *first_row = (best == -INFINITY) ? -1 : (long long)(-best);
+  *first_dist = bd;
+}
+
+// ------------------------------------------------------------------ ADMM
+struct AdmmOut { int iters; int solved; double pri, dua; };
+
+SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state = 0) {
+  AdmmOut o; o.iters = 0; o.solved = 0; o.pri = o.dua = INFINITY;
+  const int K = c.K;
+  double* red = c.sm;
+  double* x = c.wd + c.g->L.x;
+  if (!keep_state) forward_rows(c, 0);
+  const int check = c.g->pb.check_every, maxit = c.g->pb.max_admm_iter;
+  for (int it = 1; it <= maxit; ++it) {
+    const int chk = (it % check == 0) || it == maxit;
+    transpose_rows(c, 0);
+    x_update(c, chk);
+    forward_rows(c, 1);
+    double pri_col = 0.0;
+    if (with_collisions && c.ncand > 0) {
+      collision_rows(c, chk);
+      if (chk) pri_col = reduce_finish(c, 0, 0);
+    }
+    o.iters = it;
+    if (!chk) continue;
+    // ---- residuals in reference units (OSQP termination test, unscaled)
+    const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+    const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+    double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+    double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *off = c.wd + c.g->L.off;
+    const double ih = 1.0 / c.g->pb.time_step;
+    SCP_PHASE(c) {
+      double pr = 0.0, nr = 0.0;
+      for (int e = tid; e < c.Q * K; e += c.nthreads) {
+        int q = e / K, k = e - q * K;
+        double ax = x[e];
+        pr = SCP_FMAX(pr, fabs(ax - clampd(va[e], -al, al)));
+        nr = SCP_FMAX(nr, fabs(ax));
+        if (k < K - 1) {
+          double aj = (x[e + 1] - ax) * ih;
+          pr = SCP_FMAX(pr, fabs(aj - clampd(vj[e], -jl, jl)));
+          double v0q = c.v0[q];
+          pr = SCP_FMAX(pr, fabs(velrow[e] - clampd(vv[e], -vl - v0q, vl - v0q)));
+          int a2 = q & 1;
+          pr = SCP_FMAX(pr, fabs(posrow[e] - clampd(vp[e], lo[a2] - off[e], hi[a2] - off[e])));
+          nr = SCP_FMAX(nr, SCP_FMAX(fabs(aj), SCP_FMAX(fabs(velrow[e]), fabs(posrow[e]))));
+        }
+      }
+      red[tid] = pr; red[RED + tid] = nr;
+    }
+    SCP_SYNC(c);
+    double pri = reduce_finish(c, 0, 0);
+    double npri = reduce_finish(c, 1, 0);
+    pri = SCP_FMAX(pri, pri_col);
+    transpose_rows(c, 1);      // rhs <- 2x + A'y + C'mu
+    const double* dres = c.wd + c.g->L.rhs;
+    SCP_PHASE(c) {
+      double du = 0.0, nd = 0.0;
+      for (int e = tid; e < c.Q * K; e += c.nthreads) {
+        du = SCP_FMAX(du, fabs(dres[e]));
+        nd = SCP_FMAX(nd, SCP_FMAX(fabs(2.0 * x[e]), fabs(dres[e] - 2.0 * x[e])));
+      }
+      red[tid] = du; red[RED + tid] = nd;
+    }
+    SCP_SYNC(c);
+    double dua = reduce_finish(c, 0, 0);
+    double ndua = reduce_finish(c, 1, 0);
+    o.pri = pri; o.dua = dua;
+    if (pri <= c.g->pb.eps_abs + c.g->pb.eps_rel * npri && dua <= c.g->pb.eps_abs + c.g->pb.eps_rel * ndua) { o.solved = 1; break; }
+    if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
+    if (c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
+      double est = sqrt((pri / SCP_FMAX(npri, 1e-12)) / SCP_FMAX(dua / SCP_FMAX(ndua, 1e-12), 1e-12));
+      if (est > 5.0 || est < 0.2) {
+        est = clampd(est, 1e-2, 1e2);
+        double nrho = clampd(c.rho * est, 1e-6, 1e6);
+        est = nrho / c.rho;
+        // keep y: v = z + y/rho  ->  v = z + (v - z)/est
+        SCP_PHASE(c) {
+          for (int e = tid; e < c.Q * K; e += c.nthreads) {
+            int q = e / K, k = e - q * K;
+            double v = va[e], z = clampd(v, -al, al); va[e] = z + (v - z) / est;
+            if (k < K - 1) {
+              v = vj[e]; z = clampd(v, -jl, jl); vj[e] = z + (v - z) / est;
+              double v0q = c.v0[q];
+              v = vv[e]; z = clampd(v, -vl - v0q, vl - v0q); vv[e] = z + (v - z) / est;
+              int a2 = q & 1;
+              v = vp[e]; z = clampd(v, lo[a2] - off[e], hi[a2] - off[e]); vp[e] = z + (v - z) / est;
+            }
+          }
+        }
+        SCP_SYNC(c);
+        c.rho = nrho;
+        factor_operator(c);
+      }
+    }
+  }
+  return o;
+}
+
+// ------------------------------------------------------------------ outputs
+// scp.py:168-175: positions/velocities for k = 0..K-1 (state k), reference layout (N,K,2).
+SCP_DEV void write_outputs(Ctx& c) {
+  const int K = c.K;
+  const double* x = c.wd + c.g->L.x;
+  const double* P = c.wd + c.g->L.P;
+  const double* velrow = c.wd + c.g->L.velrow;
+  SCP_PHASE(c) {
+    for (int e = tid; e < c.Q * K; e += c.nthreads) {
+      int q = e / K, k = e - q * K, i = q >> 1, ax = q & 1;
+      size_t o = ((size_t)i * K + k) * 2 + ax;
+      c.acc[o] = x[e];
+      c.pos[o] = P[e];
+      c.vel[o] = (k == 0) ? c.v0[q] : c.v0[q] + velrow[e - 1];
+    }
+  }
+  SCP_SYNC(c);
+}
+
+// ------------------------------------------------------------------ the SCP loop
+SCP_DEV void solve_scenario(Ctx& c) {
+  const int K = c.K, N = c.N;
+  double* red = c.sm;
+  scp_b200_record r;
+  r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
+  r.admm_iterations = 0; r.qp_unsolved = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
+  r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
+  r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
+  r.cand_row_iters = 0;
+  for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
+
+  setup_scenario(c);
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0;
+  factor_operator(c);
+  AdmmOut a0 = admm_run(c, 0, 0);                       // QP #0, scp.py:138
+  r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
+  if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
+  forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
+  double minsep; long long frow; double fdist;
+  gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
+  int feasible = frow < 0;
+  r.initial_feasible = feasible;
+  if (!feasible) {
+    long long npairs = (long long)N * (N - 1) / 2;
+    int k = (int)(frow / npairs); long long p = frow - (long long)k * npairs;
+    int i = 0; while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
+    r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = i + 1 + (int)p;
+    r.first_violation_dist = fdist;
+    if (k == 0) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
+  }
+  int it = 0, converged = 0;
+  double* x = c.wd + c.g->L.x;
+  double* xprev = c.wd + c.g->L.xprev;
+  double* P = c.wd + c.g->L.P;
+  double* Pb = c.wd + c.g->L.Pbar;
+  while (r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
+    SCP_PHASE(c) {
+      for (int e = tid; e < c.Q * K; e += c.nthreads) { Pb[e] = P[e]; xprev[e] = x[e]; }
+    }
+    SCP_SYNC(c);
+    AdmmOut a; a.iters = 0; a.solved = 0; a.pri = a.dua = 0;
+    mark_near_rows(c, c.g->pb.cand_margin);
+    c.rho = c.g->pb.rho0;
+    int have_state = 0;
+    for (int attempt = 0;; ++attempt) {
+      int old_copies = c.copies;
+      build_candidates(c);
+      if (c.copies > r.max_copies) r.max_copies = c.copies;
+      if (!have_state || c.copies != old_copies) factor_operator(c);
+      a = admm_run(c, 1, have_state);                  // QP #t, scp.py:155
+      have_state = 1;
+      r.admm_iterations += a.iters;
+      r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;
+      int bad = (c.ncand < N * (N - 1) * (K - 1)) ? verify_rows(c, c.g->pb.verify_tol) : 0;
+      if (bad == 0 || attempt >= 20) break;
+      r.rebuilds++;
+    }
+    if (!a.solved) r.qp_unsolved++;
+    r.pri_res = a.pri; r.dua_res = a.dua;
+    // rel step on accelerations, scp.py:157-163
+    SCP_PHASE(c) {
+      double s0 = 0, s1 = 0;
+      for (int e = tid; e < c.Q * K; e += c.nthreads) { double d = x[e] - xprev[e]; s0 += d * d; s1 += xprev[e] * xprev[e]; }
+      red[tid] = s0; red[RED + tid] = s1;
+    }
+    SCP_SYNC(c);
+    double dn = reduce_finish(c, 0, 1), pn = reduce_finish(c, 1, 1);
+    double rel = sqrt(dn) / sqrt(pn);
+    if (it < SCP_B200_MAX_SCP_ITER) r.rel_step[it] = rel;
+    if (rel <= c.g->pb.scp_tolerance) converged = 1;
+    ++it;
+  }
+  r.scp_iterations = it; r.converged = converged;
+  forward_rows(c, 0);
+  gate_and_minsep(c, &minsep, &frow, &fdist);
+  r.min_separation = minsep;
+  SCP_PHASE(c) {
+    double s = 0;
+    for (int e = tid; e < c.Q * K; e += c.nthreads) s += x[e] * x[e];
+    red[tid] = s;
+  }
+  SCP_SYNC(c);
+  r.objective = reduce_finish(c, 0, 1);
+  write_outputs(c);
+  SCP_PHASE(c) { if (tid == 0) *c.rec = r; }
+  SCP_SYNC(c);
+}
+
+}  // namespace scp
+#endif

@@ -1,0 +1,141 @@
+"""``SCP`` -- same class, constructor, setters and ``generate_trajectories`` contract as the
+reference (src/path_planning/solvers/scp.py:31-180); the compute runs on the GPU.
+
+What stays on the host: argument checks, the prints the reference makes, the result dict.
+What moved to the device (one call, no host round trip inside): the constant operators
+(:182-257), the initial QP (:323-369), state reconstruction (:371-397, :559-595), the
+feasibility gate (:597-615), collision linearisation (:453-557), every per-iteration QP
+(:399-451) and the convergence loop (:152-166).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from .. import _capi
+
+
+class SCP:
+    def __init__(self, n_vehicles=5, time_horizon=3.0, time_step=0.1, min_distance=0.1, space_dims=None):
+        self.N = n_vehicles
+        self.T = time_horizon
+        self.h = time_step
+        self.K = int(self.T / self.h)
+        self.R = min_distance
+        if space_dims is None:
+            space_dims = [0, 0, 20, 20]
+        self.space_dims = space_dims
+        self.convergence_tolerance = 1.5e-2
+        self.trajectories = None
+        self.initial_positions = None
+        self.initial_velocities = None
+        self.final_positions = None
+        self.final_velocities = None
+        self.pos_min = np.array([space_dims[0], space_dims[1]])
+        self.pos_max = np.array([space_dims[2], space_dims[3]])
+        self.vel_min, self.vel_max = -2, 2
+        self.acc_min, self.acc_max = -15.0, 15.0
+        self.jerk_min, self.jerk_max = -20, 20
+        # new, additive: solver settings (fields of scp_b200_problem), device index, last record
+        self.solver_settings = {}
+        self.device = 0
+        self.verbose = True
+        self.last_record = None
+        self._say("---=== SCP Problem initialized ===---")
+        self._say(f"Number of timesteps: {self.K}")
+        self._say(f"Timestep: {self.h}")
+        self._say(f"Minimum distance between vehicles: {self.R}")
+        self._say(f"Space dimensions: {self.space_dims}")
+
+    def _say(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def set_initial_states(self, positions, velocities=None):
+        if velocities is None:
+            velocities = np.zeros((self.N, 2))
+        self.initial_positions = np.asarray(positions, dtype=float).flatten()
+        self.initial_velocities = np.asarray(velocities, dtype=float).flatten()
+        assert len(self.initial_positions) == len(self.initial_velocities) == 2 * self.N, (
+            f"Initial states mismatch positions={len(self.initial_positions)}, "
+            f"velocities={len(self.initial_velocities)}, expected={2*self.N}"
+        )
+
+    def set_final_states(self, positions, velocities=None):
+        if velocities is None:
+            velocities = np.zeros((self.N, 2))
+        self.final_positions = np.asarray(positions, dtype=float).flatten()
+        self.final_velocities = np.asarray(velocities, dtype=float).flatten()
+        assert len(self.final_positions) == len(self.final_velocities) == 2 * self.N, (
+            f"Final states mismatch positions={len(self.final_positions)}, "
+            f"velocities={len(self.final_velocities)}, expected={2*self.N}"
+        )
+
+    def _problem(self, max_iterations):
+        p = _capi.default_problem(self.N, self.T, self.h, self.R, self.space_dims)
+        p.n_steps = self.K
+        p.vel_limit = float(self.vel_max)
+        p.acc_limit = float(self.acc_max)
+        p.jerk_limit = float(self.jerk_max)
+        p.scp_tolerance = float(self.convergence_tolerance)
+        p.max_scp_iter = int(max_iterations)
+        for k, v in self.solver_settings.items():
+            setattr(p, k, v)
+        return p
+
+    def generate_trajectories(self, max_iterations=15):
+        """Main method to generate collision-free trajectories using SCP (device side)."""
+        lib = _capi.load()
+        start = time.time()
+        if max_iterations > _capi.MAX_SCP_ITER:
+            raise ValueError(f"max_iterations > {_capi.MAX_SCP_ITER} not supported")
+        p = self._problem(max_iterations)
+        N, K = self.N, self.K
+        buf = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        p0, v0 = buf(self.initial_positions), buf(self.initial_velocities)
+        pf, vf = buf(self.final_positions), buf(self.final_velocities)
+        acc = np.empty((N, K, 2))
+        pos = np.empty((N, K, 2))
+        vel = np.empty((N, K, 2))
+        rec = _capi.Record()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _capi.check(lib.scp_b200_solve_batch_host(C.byref(p), 1, ptr(p0), ptr(v0), ptr(pf), ptr(vf), ptr(acc),
+                                                  ptr(pos), ptr(vel), C.cast(C.byref(rec), C.c_void_p),
+                                                  int(self.device)))
+        r = _capi.record_to_dict(rec)
+        self.last_record = r
+        if r["status"] == _capi.STATUS_INITIAL_QP_FAILED:
+            print("not feasible")
+            raise RuntimeError("OSQP failed: initial QP not solved (device ADMM hit its iteration limit)")
+        if not r["initial_feasible"]:
+            k, i, j = r["first_violation"]
+            self._say(f"Avoidance constraint violation at timestep {k} between vehicles {i} and {j}: "
+                      f"distance = {r['first_violation_dist']:.3f}")
+        for it, rel in enumerate(r["rel_steps"]):
+            self._say(f"SCP Iteration {it+1}")
+            self._say(rel)
+            if rel <= self.convergence_tolerance:
+                self._say(f"Converged after {it+1} iterations.")
+        if r["qp_unsolved"]:
+            self._say(f"Warning: {r['qp_unsolved']} subproblem(s) hit the ADMM iteration limit")
+        self.trajectories = {"positions": pos, "velocities": vel, "accelerations": acc}
+        self._say(f"Trajectory generation completed in {time.time() - start:.3f} seconds")
+        return self.trajectories
+
+    # Plotting is out of scope for acceleration; thin pass-throughs keep the entry points alive.
+    def visualize_trajectories(self, show_animation=False, save_path="trajectories.pdf"):
+        if self.trajectories is None:
+            raise ValueError("Trajectories not generated yet")
+        from ..viz import _plots
+
+        return _plots.trajectories(self, show_animation, save_path)
+
+    def visualize_time_snapshots(self, num_snapshots=5, save_path=None):
+        if self.trajectories is None:
+            raise ValueError("Trajectories not generated yet")
+        from ..viz import _plots
+
+        return _plots.snapshots(self, num_snapshots, save_path)

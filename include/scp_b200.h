@@ -1,0 +1,150 @@
+/*
+ * scp_b200.h -- C ABI of the B200-native SCP trajectory solver.
+ *
+ * Drop-in boundary for ONE path of jankammeth/BA-path-planning:
+ *   SCP.generate_trajectories  (src/path_planning/solvers/scp.py:131-180)
+ * and the private helpers it calls.  The reference has no FFI of its own (it is
+ * pure Python calling the third-party `osqp` C core at scp.py:360-362 and
+ * scp.py:441-445); each entry point below names the reference code it replaces.
+ * The reference-side binding is a ctypes stub, shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - every function returns 0 on success, non-zero on error; the message of the
+ *     last error of the calling thread is returned by scp_b200_last_error();
+ *   - "d_" pointers are device pointers owned by the caller (PyTorch in the
+ *     Python host), "h_" pointers are host pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - all real data is IEEE double, the reference's dtype (numpy float64);
+ *   - trajectories use the reference layout (N, K, 2): agent-major, then time,
+ *     then x/y (scp.py:141,168,171-175); a batch adds a leading B.
+ */
+#ifndef SCP_B200_H
+#define SCP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCP_B200_ABI_VERSION 1
+#define SCP_B200_MAX_SCP_ITER 32
+
+/* Problem definition shared by every scenario of a batch.
+ * Mirrors SCP.__init__ (scp.py:32-97) + the solver settings that the reference
+ * leaves at OSQP defaults. */
+typedef struct scp_b200_problem {
+  int32_t n_agents;        /* N           scp.py:40 */
+  int32_t n_steps;         /* K=int(T/h)  scp.py:43 */
+  double time_step;        /* h           scp.py:42 */
+  double min_distance;     /* R           scp.py:44 */
+  double space[4];         /* xmin,ymin,xmax,ymax  scp.py:47-49,63-64 */
+  double vel_limit;        /* 2.0   scp.py:67-68 */
+  double acc_limit;        /* 15.0  scp.py:70-71 */
+  double jerk_limit;       /* 20.0  scp.py:73-74 */
+  double scp_tolerance;    /* 1.5e-2 scp.py:52 */
+  double feas_margin;      /* 0.01: gate distance < R - margin, scp.py:610 */
+  int32_t max_scp_iter;    /* 15    scp.py:131 */
+  /* QP solver (replaces osqp, scp.py:326-367 and 441-451) */
+  int32_t max_admm_iter;   /* per ADMM run */
+  int32_t check_every;     /* residual test period */
+  int32_t adapt_every;     /* rho adaptation period */
+  int32_t polish;          /* 1: active-set polish with KKT certificate */
+  double eps_abs, eps_rel; /* residual tolerances */
+  double rho0, sigma;      /* step size, x-proximal weight */
+  double w_jerk, w_acc, w_vel, w_pos, w_col; /* row-class weights (unit rho) */
+  double cand_margin;      /* collision rows kept when prev. distance < R + margin */
+  double verify_tol;       /* dropped rows must hold to this tolerance */
+} scp_b200_problem;
+
+/* Per-scenario result record (device or host array of B records). */
+typedef struct scp_b200_record {
+  int32_t status;          /* SCP_B200_STATUS_* */
+  int32_t scp_iterations;  /* trips of the loop scp.py:152-166 */
+  int32_t converged;       /* rel step <= tol reached */
+  int32_t initial_feasible;/* gate scp.py:144 passed (loop skipped) */
+  int32_t admm_iterations; /* total over all subproblems */
+  int32_t qp_unsolved;     /* subproblems that hit max_admm_iter (reference: warning only, scp.py:446-447) */
+  int32_t rebuilds;        /* candidate-set enlargements */
+  int32_t max_copies;      /* largest per-(agent,step) candidate count */
+  int32_t first_violation[3]; /* k,i,j of the gate's first violation, -1 if none */
+  int32_t polish_ok;       /* subproblems that ended with a KKT certificate */
+  double first_violation_dist;
+  double min_separation;   /* of the returned positions, k in [0,K) */
+  double objective;        /* sum ||a||^2 of the returned accelerations */
+  double pri_res, dua_res; /* of the last subproblem */
+  double cand_row_iters;   /* sum over ADMM iterations of collision rows actually carried */
+  double rel_step[SCP_B200_MAX_SCP_ITER]; /* scp.py:157-160, one per trip */
+} scp_b200_record;
+
+enum {
+  SCP_B200_STATUS_OK = 0,
+  SCP_B200_STATUS_INITIAL_QP_FAILED = 1, /* reference raises RuntimeError, scp.py:363-365 */
+  SCP_B200_STATUS_START_TOO_CLOSE = 2,   /* some ||p0_i-p0_j|| < R: the k=0 rows (scp.py:487-496) are infeasible */
+  SCP_B200_STATUS_NOT_RUN = -1
+};
+
+int scp_b200_abi_version(void);
+/* sizeof(scp_b200_problem) / sizeof(scp_b200_record): lets a foreign binding check its struct layout. */
+size_t scp_b200_sizeof_problem(void);
+size_t scp_b200_sizeof_record(void);
+const char* scp_b200_last_error(void);
+
+/* Fill `prob` with the reference's defaults (scp.py:32-74, OSQP-free settings). */
+void scp_b200_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon,
+                              double time_step, double min_distance);
+
+/* Constant operator tables for one (K, h, weights): replaces the constant part of
+ * _precompute_constraint_matrices (scp.py:182-232).  Host computes, then uploads. */
+size_t scp_b200_tables_bytes(const scp_b200_problem* prob);
+int scp_b200_build_tables(const scp_b200_problem* prob, void* d_tables, void* stream);
+
+/* Scratch for `slots` concurrently resident scenarios (one CTA each). */
+size_t scp_b200_workspace_bytes(const scp_b200_problem* prob, int slots);
+int scp_b200_default_slots(const scp_b200_problem* prob);
+
+/* The whole of SCP.generate_trajectories (scp.py:131-180) for B independent
+ * scenarios, device buffers, one launch, no host round trip inside.
+ *   d_p0,d_v0,d_pf,d_vf : (B,N,2)   set_initial_states / set_final_states, scp.py:99-129
+ *   d_acc,d_pos,d_vel   : (B,N,K,2) the result dict, scp.py:171-175
+ *   d_records           : B records */
+int scp_b200_solve_batch(const scp_b200_problem* prob, int n_scenarios,
+                         const double* d_p0, const double* d_v0, const double* d_pf,
+                         const double* d_vf, const void* d_tables, void* d_workspace,
+                         size_t workspace_bytes, int slots, double* d_acc, double* d_pos,
+                         double* d_vel, scp_b200_record* d_records, void* stream);
+
+/* Same, host buffers: allocates device memory, copies in, solves, copies out.
+ * This is the call a non-PyTorch host (or the reference's own SCP class through
+ * ctypes) makes; it is what bench.py's "e2e" figure times. */
+int scp_b200_solve_batch_host(const scp_b200_problem* prob, int n_scenarios, const double* h_p0,
+                              const double* h_v0, const double* h_pf, const double* h_vf,
+                              double* h_acc, double* h_pos, double* h_vel,
+                              scp_b200_record* h_records, int device);
+
+/* _compute_positions_velocities / _accelerations_to_positions_velocities
+ * (scp.py:371-397, 559-595): (B,N,K,2) accelerations -> positions, velocities. */
+int scp_b200_reconstruct(const double* d_acc, const double* d_p0, const double* d_v0, int n_scenarios,
+                         int n_agents, int n_steps, double time_step, double* d_pos, double* d_vel,
+                         void* stream);
+
+/* Collision linearisation, _add_collision_constraints (scp.py:453-557), matrix
+ * free: for every row (k, i<j) in the reference's order (k-major, then i<j
+ * lexicographic) writes eta (2 doubles) and the bound of
+ *     eta . (p_i[k] - p_j[k]) >= bound          
+ * and reduces the minimum separation per scenario (the quantity tested by
+ * _fast_check_avoidance_constraints, scp.py:597-615) plus the first violating
+ * row in scan order.
+ *   d_pos   : (B,N,K,2)          d_eta : (B,K,P,2)   d_bound : (B,K,P)   P = N(N-1)/2
+ *   d_minsep: (B)                d_first: (B,3) int32 (k,i,j or -1)
+ * d_eta / d_bound may be NULL (reduction only). */
+int scp_b200_linearize(const double* d_pos, int n_scenarios, int n_agents, int n_steps,
+                       double min_distance, double feas_margin, double* d_eta, double* d_bound,
+                       double* d_minsep, int32_t* d_first, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCP_B200_H */

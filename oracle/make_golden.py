@@ -1,0 +1,96 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+For every (N, seed) case it runs the VERBATIM reference scp.py (loaded by
+oracle/ref_loader.py with the osqp/matplotlib shims) in truth mode -- ADMM to
+1e-5 then active-set refinement with a KKT certificate -- and, beside it, the
+numpy restatement oracle/scp_oracle.py; the two must agree to 1e-9 and every
+subproblem must carry a certificate <= 1e-9, otherwise the case is rejected.
+Stored: inputs, the certified iterates/outputs, and the same scenario solved at
+OSQP's default eps 1e-3 (how far the loose reference itself sits from the minimiser).
+"""
+
+from __future__ import annotations
+
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, scp_oracle  # noqa: E402
+
+CASES = [  # name, N, T, h, R, space, seed (None: explicit positions)
+    ("n5_s0", 5, 10.0, 0.2, 0.8, [0, 0, 20, 20], 0),
+    ("n5_s1", 5, 10.0, 0.2, 0.8, [0, 0, 20, 20], 1),
+    ("n8_s1", 8, 10.0, 0.2, 0.8, [0, 0, 20, 20], 1),
+    ("n10_s1", 10, 10.0, 0.2, 0.8, [0, 0, 20, 20], 1),
+    ("n10_s2", 10, 10.0, 0.2, 0.8, [0, 0, 20, 20], 2),
+    ("n15_s2", 15, 10.0, 0.2, 0.8, [0, 0, 20, 20], 2),
+    ("n25_s3", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 3),
+    ("n25_s10000", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 10000),
+]
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def run_reference(ref, N, T, h, R, space, p0, pf, overrides):
+    import osqp
+
+    osqp.OVERRIDES.clear()
+    osqp.OVERRIDES.update(overrides)
+    osqp.STATS.clear()
+    with ref_loader.quiet() as buf:
+        s = ref.solvers.scp.SCP(n_vehicles=N, time_horizon=T, time_step=h, min_distance=R, space_dims=space)
+        s.set_initial_states(p0)
+        s.set_final_states(pf)
+        tr = s.generate_trajectories(max_iterations=15)
+    rels = [float(x) for x in buf.getvalue().splitlines() if x and (x[0].isdigit() or x.startswith("nan"))]
+    stats = list(osqp.STATS)
+    osqp.OVERRIDES.clear()
+    return tr, rels, stats
+
+
+def main(only=None):
+    ref = ref_loader.load_reference()
+    gen = ref.scenarios.position_generator.generate_positions
+    truth = dict(eps_abs=1e-5, eps_rel=1e-5, max_iter=200000, certify=True)
+    for name, N, T, h, R, space, seed in CASES:
+        if only and name not in only:
+            continue
+        path = os.path.join(OUT, f"{name}.npz")
+        if os.path.exists(path):
+            continue
+        t0 = time.time()
+        random.seed(seed)
+        np.random.seed(seed)
+        p0, pf = gen(N, R)
+        tr, rels, stats = run_reference(ref, N, T, h, R, space, p0, pf, truth)
+        certs = [s["cert"] for s in stats]
+        assert all(s["polish"] == 1 and s["cert"] <= 1e-9 for s in stats), (name, certs)
+        osqp = scp_oracle._osqp()
+        osqp.OVERRIDES.update(truth)
+        o = scp_oracle.ScpOracle(N, T, h, R, space)
+        o.set_initial_states(p0)
+        o.set_final_states(pf)
+        tro = o.generate_trajectories(15)
+        osqp.OVERRIDES.clear()
+        for k in ("positions", "velocities", "accelerations"):
+            assert np.abs(tr[k] - tro[k]).max() <= 1e-9, (name, k)
+        loose, rels_loose, _ = run_reference(ref, N, T, h, R, space, p0, pf, {})
+        np.savez_compressed(
+            path, N=N, T=T, h=h, R=R, space=np.array(space, float), seed=seed, p0=p0, pf=pf,
+            positions=tr["positions"], velocities=tr["velocities"], accelerations=tr["accelerations"],
+            rel_steps=np.array(rels), iterations=len(rels), certs=np.array(certs),
+            a_initial=o.record["a_initial"], iterates=np.array(o.record["iterates"]),
+            objective=float((tr["accelerations"] ** 2).sum()), min_separation=scp_oracle.min_separation(tr["positions"]),
+            loose_positions=loose["positions"], loose_accelerations=loose["accelerations"],
+            loose_rel_steps=np.array(rels_loose),
+        )
+        print(f"{name}: {len(rels)} SCP iterations, max cert {max(certs):.1e}, {time.time()-t0:.0f}s", flush=True)
+
+
+if __name__ == "__main__":
+    main(set(sys.argv[1:]) or None)

@@ -110,8 +110,8 @@ class ScpOracle:
         self.l_acc = np.full(2 * N * K, self.acc_min)
         self.u_acc = np.full(2 * N * K, self.acc_max)
         T, S = integrator_blocks(K, h)
-        self.C_vel = sp.kron(IN, h * sp.kron(sp.csc_matrix(T), I2), format="csc")
-        self.C_pos = sp.kron(IN, sp.kron(sp.csc_matrix(S), I2), format="csc")
+        self.C_vel = sp.kron(IN, h * sp.kron(sp.csc_matrix(T), I2, format="csc"), format="csc")
+        self.C_pos = sp.kron(IN, sp.kron(sp.csc_matrix(S), I2, format="csc"), format="csc")
 
         p0 = self.initial_positions.reshape(N, 2)
         v0 = self.initial_velocities.reshape(N, 2)
@@ -261,7 +261,7 @@ class ScpOracle:
     def generate_trajectories(self, max_iterations=15):
         """scp.py:131-180."""
         t0 = time.perf_counter()
-        self.record = {"rel_steps": [], "qp": []}
+        self.record = {"rel_steps": [], "qp": [], "iterates": []}
         self.precompute_constraint_matrices()
         a = self.solve_initial_trajectory()
         pos0, _ = self.states_from_accelerations(a)
@@ -276,6 +276,7 @@ class ScpOracle:
             if rel <= self.convergence_tolerance:
                 converged = True
             a = a_new
+            self.record["iterates"].append(a.copy())
             iteration += 1
         acc = a.reshape(self.N, self.K, 2)
         pos, vel = self.states_from_accelerations(acc)

@@ -366,7 +366,8 @@ class OSQP:
         STATS.append(
             dict(n=n, m=m, iter=it, status=status, pri=float(pri), dua=float(dua), rho=self.rho,
                  rho_updates=rho_updates, setup_s=self.setup_time, solve_s=info.solve_time,
-                 polish=info.status_polish, cert=info.kkt_certificate)
+                 polish=info.status_polish, cert=info.kkt_certificate,
+                 refine_rounds=getattr(self, "_refine_rounds", 0), n_active=getattr(self, "_refine_nact", 0))
         )
         return res
 
@@ -427,10 +428,14 @@ class OSQP:
         Acsr = A.tocsr()
         scale_p = 1.0 + max(np.max(np.abs(Ax)), 1.0)
         best = (np.inf, x, y)
+        self._refine_rounds = 0
+        self._refine_nact = 0
         for _ in range(max_rounds):
+            self._refine_rounds += 1
             act = np.flatnonzero(eq | low | upp)
             b = np.where(upp[act], u[act], l[act])
             Aa = Acsr[act]
+            self._refine_nact = len(act)
             if diagP:
                 Aad = Aa.toarray()
                 G = (Aad / pd) @ Aad.T

@@ -1,0 +1,44 @@
+// TEST-ONLY host emulation of the kernel source (csrc/scp_device.inl compiled as
+// plain C++ with SCP_EMU: a phase = a sequential loop over thread ids).  It
+// exists to debug the solver logic in a container without a GPU.  The product
+// package never builds, loads or falls back to this file.
+#define SCP_EMU 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../ba-path-planning_b200/csrc/scp_device.inl"
+#include "../../ba-path-planning_b200/csrc/scp_tables.h"
+
+extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const double* p0, const double* v0,
+                                   const double* pf, const double* vf, double* acc, double* pos,
+                                   double* vel, scp_b200_record* rec, int nthreads) {
+  using namespace scp;
+  const int N = prob->n_agents, K = prob->n_steps;
+  HostTables ht = build_host_tables(*prob);
+  Params g;
+  g.pb = *prob;
+  g.L = make_layout(N, K);
+  const double* tb = ht.blob.data();
+  g.tb.B1 = tb + ht.oB1; g.tb.B2 = tb + ht.oB2; g.tb.rj = tb + ht.orj; g.tb.ra = tb + ht.ora;
+  g.tb.rv = tb + ht.orv; g.tb.rp = tb + ht.orp; g.tb.rc = tb + ht.orc;
+  std::vector<double> wd(g.L.n_double, 0.0);
+  std::vector<int> wi(g.L.n_int, 0);
+  std::vector<double> sm(4 * RED + (size_t)K * K, 0.0);
+  for (int b = 0; b < B; ++b) {
+    Ctx c;
+    c.nthreads = nthreads; c.N = N; c.K = K; c.Q = 2 * N; c.g = &g;
+    c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1;
+    size_t s2 = (size_t)b * N * 2, s3 = (size_t)b * N * K * 2;
+    c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
+    c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
+    solve_scenario(c);
+  }
+  return 0;
+}
+
+extern "C" void scp_emu_default_problem(scp_b200_problem* p, int n, double T, double h, double R);
+#include "../../ba-path-planning_b200/csrc/scp_defaults.h"
+extern "C" void scp_emu_default_problem(scp_b200_problem* p, int n, double T, double h, double R) {
+  scp_fill_default_problem(p, n, T, h, R);
+}

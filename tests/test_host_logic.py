@@ -1,0 +1,90 @@
+"""Host-side logic on CPU: reference-facing class surface, batch records/summary schema, tables,
+and the N>1 scenario sharding with a world_size-2 gloo group."""
+import io
+import os
+import contextlib
+
+import numpy as np
+import pytest
+
+from path_planning import SCP
+from path_planning.cli import compute_trajectories_batch as ctb
+from path_planning.solvers.sharding import shard_range
+
+
+def test_scp_surface_matches_reference():
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        s = SCP(n_vehicles=10, time_horizon=100, time_step=0.2, min_distance=0.8, space_dims=[0, 0, 200, 200])
+    assert buf.getvalue().splitlines()[0] == "---=== SCP Problem initialized ===---"
+    assert len(buf.getvalue().splitlines()) == 5
+    assert (s.N, s.K, s.T, s.h, s.R) == (10, 500, 100, 0.2, 0.8)
+    assert s.convergence_tolerance == 1.5e-2 and (s.vel_max, s.acc_max, s.jerk_max) == (2, 15.0, 20)
+    assert np.array_equal(s.pos_max, [200, 200]) and s.trajectories is None
+    s.set_initial_states(np.zeros((10, 2)))
+    assert s.initial_velocities.shape == (20,)
+    with pytest.raises(AssertionError):
+        s.set_final_states(np.zeros((9, 2)))
+    with pytest.raises(ValueError):
+        s.visualize_trajectories()
+    with pytest.raises(ValueError):
+        s.visualize_time_snapshots()
+
+
+def test_batch_config_and_summary_schema():
+    assert set(["Ns", "trials_per_N", "time_horizon", "time_step", "min_distance", "space_dims", "max_iterations",
+                "rng_seed", "results_dir"]) <= set(ctb.CONFIG)
+    runs = [dict(N=5, status="success", time_sec=t) for t in (1.0, 2.0, 4.0)] + [dict(N=5, status="error", time_sec=9.0)]
+    s = ctb.summarize(runs, [5, 7])
+    assert s["5"]["count"] == 3 and s["5"]["errors"] == 1 and s["5"]["median"] == 2.0
+    assert abs(s["5"]["std"] - np.std([1, 2, 4], ddof=1)) < 1e-12
+    assert s["7"] == {"count": 0, "errors": 0, "min": None, "max": None, "mean": None, "median": None, "p25": None,
+                      "p75": None, "std": None}
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            parts = [shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from path_planning.solvers.sharding import solve_scenarios_sharded
+
+    p0 = np.arange(7 * 3 * 2, dtype=float).reshape(7, 3, 2)
+
+    def fake_solve(a, b):  # stands in for BatchSolver.solve on this rank's GPU
+        return {"positions": a.copy()}, [{"objective": float(x.sum())} for x in a]
+
+    traj, recs = solve_scenarios_sharded(fake_solve, p0, p0)
+    q.put((rank, traj["positions"].shape[0], [(r["scenario_index"], r["rank"], r["objective"]) for r in recs]))
+    dist.destroy_process_group()
+
+
+def test_scenario_sharding_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    p0 = np.arange(7 * 3 * 2, dtype=float).reshape(7, 3, 2)
+    assert [r[1] for r in res] == [4, 3]
+    for _, _, recs in res:
+        assert [r[0] for r in recs] == list(range(7))
+        assert [r[1] for r in recs] == [0, 0, 0, 0, 1, 1, 1]
+        assert np.allclose([r[2] for r in recs], p0.sum(axis=(1, 2)))
