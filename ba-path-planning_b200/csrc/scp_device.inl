@@ -804,6 +804,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       have_state = 1;
       r.admm_iterations += a.iters;
       r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;
+      if (!a.solved) break;                            // unsolved (e.g. infeasible) subproblem: keep x, like scp.py:446-449
       int bad = (c.ncand < N * (N - 1) * (K - 1)) ? verify_rows(c, c.g->pb.verify_tol) : 0;
       if (bad == 0 || attempt >= 20) break;
       r.rebuilds++;
