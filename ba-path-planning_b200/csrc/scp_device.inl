@@ -75,6 +75,9 @@ struct Tables {                 // constant per (K, h, weights); unit rho
 struct Layout {
   size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
   size_t c_eta, c_bound, lam, scr, red, n_double;
+  size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey;   // polish (doubles)
+  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn;                       // polish (ints)
+  int pcap;
   size_t cnt, coff, c_j, flags, n_int;
   size_t cap;
 };
@@ -97,12 +100,19 @@ Layout make_layout(int N, int K) {
   L.off = take(QK); L.deq = take(2 * Q); L.mu = take(2 * Q);
   L.cap = (size_t)N * (size_t)K * (size_t)(N > 1 ? N - 1 : 1);
   L.c_eta = take(2 * L.cap); L.c_bound = take(L.cap); L.lam = take((size_t)N * N * K);
-  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 8);
+  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 2 * Q + 1600);
   L.red = take(4 * RED);
+  L.pcap = 12 * N + 128; if (L.pcap > 1536) L.pcap = 1536;
+  L.xt = take(QK); L.Pt = take(QK); L.yj = take(QK); L.ya = take(QK); L.yv = take(QK); L.yp = take(QK);
+  L.plam = take(L.cap);
+  L.pL = take((size_t)L.pcap * L.pcap); L.pG = take((size_t)L.pcap * L.pcap); L.prhs = take(L.pcap); L.py = take(L.pcap); L.pb_ = take(L.pcap);
+  L.pex = take(L.pcap); L.pey = take(L.pcap);
   L.n_double = o;
   size_t p = 0;
   auto takei = [&](size_t n) { size_t r = p; p += (n + 3) & ~(size_t)3; return r; };
   L.cnt = takei((size_t)N * K + 1); L.coff = takei((size_t)N * K + 1); L.c_j = takei(L.cap); L.flags = takei(((size_t)N * N * K + 3) / 4);
+  L.pmark = takei(4 * QK); L.pcmark = takei(L.cap);
+  L.ptype = takei(L.pcap); L.pq = takei(L.pcap); L.pj2 = takei(L.pcap); L.pk = takei(L.pcap); L.psgn = takei(L.pcap);
   L.n_int = p;
   return L;
 }
@@ -162,13 +172,18 @@ SCP_DEV void setup_scenario(Ctx& c) {
   double* off = c.wd + c.g->L.off;
   double* deq = c.wd + c.g->L.deq;
   double* x = c.wd + c.g->L.x;
+  double* F = c.wd + c.g->L.F;
+  double* FY = c.wd + c.g->L.FY;
+  double* mu = c.wd + c.g->L.mu;
   const double h = c.g->pb.time_step;
   SCP_PHASE(c) {
     for (int e = tid; e < c.Q * K; e += c.nthreads) {
       int q = e / K, k = e - q * K;
       off[e] = c.p0[q] + h * (double)(k + 1) * c.v0[q];
       x[e] = 0.0;
+      F[e] = 0.0; FY[e] = 0.0;          // scratch is not zero-initialised by the caller
     }
+    for (int t = tid; t < 2 * c.Q; t += c.nthreads) mu[t] = 0.0;
     for (int q = tid; q < c.Q; q += c.nthreads) {
       deq[2 * q + 0] = c.vf[q] - c.v0[q];
       deq[2 * q + 1] = c.pf[q] - (c.p0[q] + h * (double)K * c.v0[q]);
@@ -328,6 +343,7 @@ SCP_DEV void forward_rows(Ctx& c, int mode) {
 // mode 0 (rhs of the x-update):  w = rho r (2 clip(v) - v); wp += rho c rc posrow + F; base = sigma x
 // mode 1 (dual residual):        w = rho r (v - clip(v)) = y; wp -= FY; base = 2 x + C'mu
 //   in mode 1 the result is written to rhs and max|.| terms are left to the caller.
+// mode 2 (polish):               w = y read from the dense arrays yj/ya/yv/yp, wp -= FY; base = 0
 SCP_DEV void transpose_rows(Ctx& c, int mode) {
   const int K = c.K, nch = (K + CH - 1) / CH;
   const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho;
@@ -336,6 +352,7 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
   double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
   double *posrow = c.wd + c.g->L.posrow, *off = c.wd + c.g->L.off, *mu = c.wd + c.g->L.mu;
   double* Fm = c.wd + (mode == 0 ? c.g->L.F : c.g->L.FY);
+  if (mode == 2) { vj = c.wd + c.g->L.yj; va = c.wd + c.g->L.ya; vv = c.wd + c.g->L.yv; vp = c.wd + c.g->L.yp; }
   double* t1 = c.wd + c.g->L.scr;          // chunk totals
   double* t2 = t1 + (size_t)c.Q * nch;
   double* t3 = t2 + (size_t)c.Q * nch;
@@ -365,9 +382,9 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
           double wv = 0, wp = 0;
           if (k < K - 1) {
             double v = vv[e], z = clampd(v, lv, uv);
-            wv = rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : v - z);
+            wv = mode == 2 ? v : rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : v - z);
             v = vp[e]; z = clampd(v, lo[ax] - off[e], hi[ax] - off[e]);
-            wp = rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : v - z);
+            wp = mode == 2 ? v : rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : v - z);
             // force on position state k+1 <-> row k
             if (mode == 0) wp += cpr * c.g->tb.rc[k] * posrow[e] + Fm[q * K + k + 1];
             else wp -= Fm[q * K + k + 1];
@@ -375,13 +392,13 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
           r1v += wv; r1p += wp; r2p += r1p;
           if (pass == 1) {
             double v = va[e], z = clampd(v, -al, al);
-            double o = rho * c.g->tb.ra[k] * (mode == 0 ? 2 * z - v : v - z);
+            double o = mode == 2 ? v : rho * c.g->tb.ra[k] * (mode == 0 ? 2 * z - v : v - z);
             double wj0 = 0, wj1 = 0;   // wj[k-1], wj[k]
-            if (k >= 1) { v = vj[e - 1]; z = clampd(v, -jl, jl); wj0 = rho * c.g->tb.rj[k - 1] * (mode == 0 ? 2 * z - v : v - z); }
-            if (k < K - 1) { v = vj[e]; z = clampd(v, -jl, jl); wj1 = rho * c.g->tb.rj[k] * (mode == 0 ? 2 * z - v : v - z); }
+            if (k >= 1) { v = vj[e - 1]; z = clampd(v, -jl, jl); wj0 = mode == 2 ? v : rho * c.g->tb.rj[k - 1] * (mode == 0 ? 2 * z - v : v - z); }
+            if (k < K - 1) { v = vj[e]; z = clampd(v, -jl, jl); wj1 = mode == 2 ? v : rho * c.g->tb.rj[k] * (mode == 0 ? 2 * z - v : v - z); }
             o += (wj0 - wj1) * ih + h * r1v + h * h * (r2p - 0.5 * r1p);
             if (mode == 0) o += sig * x[e];
-            else o += 2.0 * x[e] + h * mu[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * mu[2 * q + 1];
+            else if (mode == 1) o += 2.0 * x[e] + h * mu[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * mu[2 * q + 1];
             out[e] = o;
           }
         }
@@ -486,6 +503,7 @@ SCP_DEV void mark_near_rows(Ctx& c, double margin) {
   unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
   double* lam = c.wd + c.g->L.lam;
   double* F = c.wd + c.g->L.F;
+  double* FY = c.wd + c.g->L.FY;
   const double R = c.g->pb.min_distance;
   const double r2 = (R + margin) * (R + margin);
   SCP_PHASE(c) {
@@ -499,7 +517,7 @@ SCP_DEV void mark_near_rows(Ctx& c, double margin) {
         if (near) lam[(size_t)t * N + j] = 0.0;
       }
     }
-    for (int e = tid; e < c.Q * K; e += c.nthreads) F[e] = 0.0;
+    for (int e = tid; e < c.Q * K; e += c.nthreads) { F[e] = 0.0; FY[e] = 0.0; }
   }
   SCP_SYNC(c);
 }
@@ -635,16 +653,476 @@ SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, doubl
   *first_dist = bd;
 }
 
-// ------------------------------------------------------------------ ADMM
-struct AdmmOut { int iters; int solved; double pri, dua; };
+// ------------------------------------------------------------------ polish
+// Active-set refinement ("polish", OSQP paper section 4, with add/drop rounds).  Given a
+// guess W of the active rows it solves  min sum||x||^2  s.t.  C x_q = d_q, u_r.x = b_r (r in W)
+// exactly:  x = x_d - 1/2 Pi A_W' y,  (A_W Pi A_W') y = 2 (A_W x_d - b_W),
+// Pi = I - C'(CC')^-1 C, x_d = C'(CC')^-1 d.  All Gram entries are closed forms of the row
+// type and step (rows are D_k, e_k, V_k, S_k or eta-weighted S_k pairs), so G is assembled
+// without touching a K-vector.  Then every carried row is checked (violated -> add, wrong
+// multiplier sign -> drop) until W is stable: the result satisfies the KKT conditions of the
+// carried QP to rounding, i.e. it IS its minimiser.
+struct PRow { int type, q, j, k; double ex, ey; };   // type 0 jerk,1 acc,2 vel,3 pos,4 collision(i=q,j, state k)
 
-SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state = 0) {
-  AdmmOut o; o.iters = 0; o.solved = 0; o.pri = o.dua = INFINITY;
+SCP_DEV double lib_dot(int t1, int k1, int t2, int k2, double h) {
+  if (t1 > t2) { int t = t1; t1 = t2; t2 = t; t = k1; k1 = k2; k2 = t; }
+  const double h2 = h * h;
+  if (t1 == 0) {
+    if (t2 == 0) return ((k1 == k2) ? 2.0 : ((k1 == k2 + 1 || k1 + 1 == k2) ? -1.0 : 0.0)) / h2;
+    if (t2 == 1) return ((k2 == k1 + 1) ? 1.0 : ((k2 == k1) ? -1.0 : 0.0)) / h;
+    if (t2 == 2) return (k1 == k2) ? -1.0 : 0.0;
+    return (k1 + 1 <= k2) ? -h : ((k1 == k2) ? -0.5 * h : 0.0);
+  }
+  if (t1 == 1) {
+    if (t2 == 1) return (k1 == k2) ? 1.0 : 0.0;
+    if (t2 == 2) return (k1 <= k2) ? h : 0.0;
+    return (k1 <= k2) ? h2 * ((double)(k2 - k1) + 0.5) : 0.0;
+  }
+  const double n = (double)((k1 < k2 ? k1 : k2) + 1);
+  if (t1 == 2) {
+    if (t2 == 2) return h2 * n;
+    return h2 * h * (n * ((double)k2 + 0.5) - 0.5 * n * (n - 1.0));
+  }
+  const double a = (double)k1 + 0.5, b = (double)k2 + 0.5;
+  return h2 * h2 * (n * a * b - (a + b) * 0.5 * n * (n - 1.0) + (n - 1.0) * n * (2.0 * n - 1.0) / 6.0);
+}
+
+struct PGeom { double h; int K; double i00, i01, i11; };   // (CC')^-1
+
+SCP_DEV PGeom make_pgeom(double h, int K) {
+  PGeom g; g.h = h; g.K = K;
+  double h00 = lib_dot(2, K - 1, 2, K - 1, h), h01 = lib_dot(2, K - 1, 3, K - 1, h), h11 = lib_dot(3, K - 1, 3, K - 1, h);
+  double det = h00 * h11 - h01 * h01;
+  g.i00 = h11 / det; g.i01 = -h01 / det; g.i11 = h00 / det;
+  return g;
+}
+
+// u' Pi u'  for library vectors (type 4 uses S_{k-1})
+SCP_DEV double lib_proj(const PGeom& g, int t1, int k1, int t2, int k2) {
+  const double c1v = lib_dot(t1, k1, 2, g.K - 1, g.h), c1p = lib_dot(t1, k1, 3, g.K - 1, g.h);
+  const double c2v = lib_dot(t2, k2, 2, g.K - 1, g.h), c2p = lib_dot(t2, k2, 3, g.K - 1, g.h);
+  return lib_dot(t1, k1, t2, k2, g.h) - (c1v * (g.i00 * c2v + g.i01 * c2p) + c1p * (g.i01 * c2v + g.i11 * c2p));
+}
+
+SCP_DEV double gram_entry(const PGeom& g, const PRow& a, const PRow& b) {
+  if (a.type < 4 && b.type < 4) return (a.q == b.q) ? lib_proj(g, a.type, a.k, b.type, b.k) : 0.0;
+  if (a.type == 4 && b.type == 4) {
+    int sgn = (a.q == b.q) + (a.j == b.j) - (a.q == b.j) - (a.j == b.q);
+    if (sgn == 0) return 0.0;
+    return (double)sgn * (a.ex * b.ex + a.ey * b.ey) * lib_proj(g, 3, a.k - 1, 3, b.k - 1);
+  }
+  const PRow& d = a.type < 4 ? a : b;
+  const PRow& cr = a.type < 4 ? b : a;
+  const int ag = d.q >> 1;
+  double coef = (ag == cr.q) ? 1.0 : ((ag == cr.j) ? -1.0 : 0.0);
+  if (coef == 0.0) return 0.0;
+  coef *= (d.q & 1) ? cr.ey : cr.ex;
+  return coef * lib_proj(g, d.type, d.k, 3, cr.k - 1);
+}
+
+SCP_DEV PRow load_prow(Ctx& c, int r) {
+  PRow w;
+  w.type = (c.wi + c.g->L.ptype)[r]; w.q = (c.wi + c.g->L.pq)[r]; w.j = (c.wi + c.g->L.pj2)[r];
+  w.k = (c.wi + c.g->L.pk)[r]; w.ex = (c.wd + c.g->L.pex)[r]; w.ey = (c.wd + c.g->L.pey)[r];
+  return w;
+}
+
+// marks: dyn rows pmark[cls*QK + e] in {-1 lower, 0, +1 upper}; collision entries pcmark[s] in {0,1}
+// (only the i<j owner's entry is used).  Returns the number of active rows, or -1 if > cap.
+SCP_DEV int polish_compact(Ctx& c) {
+  const int K = c.K, N = c.N, QK = c.Q * K;
+  const int* pmark = c.wi + c.g->L.pmark;
+  const int* pcmark = c.wi + c.g->L.pcmark;
+  const int* coff = c.wi + c.g->L.coff;
+  const int* cj = c.wi + c.g->L.c_j;
+  int *ptype = c.wi + c.g->L.ptype, *pq = c.wi + c.g->L.pq, *pj2 = c.wi + c.g->L.pj2, *pk = c.wi + c.g->L.pk,
+      *psgn = c.wi + c.g->L.psgn;
+  double *pb = c.wd + c.g->L.pb_, *pex = c.wd + c.g->L.pex, *pey = c.wd + c.g->L.pey;
+  const double* ceta = c.wd + c.g->L.c_eta;
+  const double* cb = c.wd + c.g->L.c_bound;
+  const double* off = c.wd + c.g->L.off;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  const int total = 4 * QK + (K - 1) * N;           // dyn marks, then one unit per (k,i) owner segment
+  const int per = (total + c.nthreads - 1) / c.nthreads;
+  int* part = (int*)(c.sm + 2 * RED);
+  SCP_PHASE(c) {
+    int n = 0;
+    for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
+      if (u < 4 * QK) n += (pmark[u] != 0);
+      else {
+        int t = u - 4 * QK, k = 1 + t / N, i = t - (k - 1) * N;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) n += (cj[sidx] > i && pcmark[sidx]);
+      }
+    }
+    part[tid] = n;
+  }
+  SCP_SYNC(c);
+  int ntot = 0;
+  for (int e = 0; e < c.nthreads; ++e) ntot += part[e];
+  if (ntot > c.g->L.pcap) { SCP_SYNC(c); return -1; }
+  SCP_PHASE(c) {
+    int base = 0;
+    for (int e = 0; e < tid; ++e) base += part[e];
+    for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
+      if (u < 4 * QK) {
+        int m = pmark[u];
+        if (!m) continue;
+        int cls = u / QK, e = u - cls * QK, q = e / K, k = e - q * K;
+        ptype[base] = cls; pq[base] = q; pj2[base] = -1; pk[base] = k; psgn[base] = m; pex[base] = 0; pey[base] = 0;
+        double b;
+        if (cls == 0) b = m > 0 ? jl : -jl;
+        else if (cls == 1) b = m > 0 ? al : -al;
+        else if (cls == 2) b = (m > 0 ? vl : -vl) - c.v0[q];
+        else b = (m > 0 ? hi[q & 1] : lo[q & 1]) - off[e];
+        pb[base] = b;
+        ++base;
+      } else {
+        int t = u - 4 * QK, k = 1 + t / N, i = t - (k - 1) * N;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
+          int j = cj[sidx];
+          if (j > i && pcmark[sidx]) {
+            ptype[base] = 4; pq[base] = i; pj2[base] = j; pk[base] = k; psgn[base] = -1;
+            double ex = ceta[2 * sidx], ey = ceta[2 * sidx + 1];
+            pex[base] = ex; pey[base] = ey;
+            // eta.(p_i - p_j) >= bound with p = off[k-1] + S_{k-1} x
+            pb[base] = cb[sidx] - (ex * (off[(2 * i) * K + k - 1] - off[(2 * j) * K + k - 1]) +
+                                   ey * (off[(2 * i + 1) * K + k - 1] - off[(2 * j + 1) * K + k - 1]));
+            ++base;
+          }
+        }
+      }
+    }
+  }
+  SCP_SYNC(c);
+  return ntot;
+}
+
+// Cholesky solve of (G + delta I) y = rhs with two refinement sweeps on G.  Returns 0 on breakdown.
+SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
+  const int ld = c.g->L.pcap;
+  double* A = c.wd + c.g->L.pL;           // column-major lower triangle: A[col*ld + row]
+  double* G0 = c.wd + c.g->L.pG;          // untouched copy of G for the refinement residual
+  double* rhs = c.wd + c.g->L.prhs;
+  double* y = c.wd + c.g->L.py;
+  const double* pb = c.wd + c.g->L.pb_;
+  const double* deq = c.wd + c.g->L.deq;
+  double* red = c.sm;
+  // assemble G (lower) and rhs = 2 (A_W x_d - b)
+  SCP_PHASE(c) {
+    double dmax = 0.0;
+    for (int e = tid; e < n * n; e += c.nthreads) {
+      int col = e / n, row = e - col * n;
+      if (row < col) continue;
+      PRow a = load_prow(c, row), b = load_prow(c, col);
+      double v = gram_entry(g, a, b);
+      A[(size_t)col * ld + row] = v;
+      G0[(size_t)col * ld + row] = v;
+      if (row == col) dmax = SCP_FMAX(dmax, v);
+    }
+    for (int r = tid; r < n; r += c.nthreads) {
+      PRow a = load_prow(c, r);
+      double axd = 0.0;
+      if (a.type < 4) {
+        double cv = lib_dot(a.type, a.k, 2, g.K - 1, g.h), cp = lib_dot(a.type, a.k, 3, g.K - 1, g.h);
+        double d0 = deq[2 * a.q], d1 = deq[2 * a.q + 1];
+        axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
+      } else {
+        double cv = lib_dot(3, a.k - 1, 2, g.K - 1, g.h), cp = lib_dot(3, a.k - 1, 3, g.K - 1, g.h);
+        double d0 = a.ex * (deq[2 * (2 * a.q)] - deq[2 * (2 * a.j)]) + a.ey * (deq[2 * (2 * a.q + 1)] - deq[2 * (2 * a.j + 1)]);
+        double d1 = a.ex * (deq[2 * (2 * a.q) + 1] - deq[2 * (2 * a.j) + 1]) + a.ey * (deq[2 * (2 * a.q + 1) + 1] - deq[2 * (2 * a.j + 1) + 1]);
+        axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
+      }
+      rhs[r] = 2.0 * (axd - pb[r]);
+      y[r] = 0.0;
+    }
+    red[tid] = dmax;
+  }
+  SCP_SYNC(c);
+  const double delta = 1e-11 * SCP_FMAX(reduce_finish(c, 0, 0), 1e-300);
+  int ok = 1;
+  for (int j = 0; j < n; ++j) {
+    SCP_PHASE(c) {
+      for (int i = j + tid; i < n; i += c.nthreads) {
+        double sacc = A[(size_t)j * ld + i] + (i == j ? delta : 0.0);
+        for (int k = 0; k < j; ++k) sacc -= A[(size_t)k * ld + i] * A[(size_t)k * ld + j];
+        A[(size_t)j * ld + i] = sacc;
+      }
+    }
+    SCP_SYNC(c);
+    const double piv = A[(size_t)j * ld + j];
+    if (!(piv > 0.0)) { ok = 0; }
+    const double d = ok ? sqrt(piv) : 1.0;
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      for (int i = j + 1 + tid; i < n; i += c.nthreads) A[(size_t)j * ld + i] /= d;
+      if (tid == 0) A[(size_t)j * ld + j] = d;
+    }
+    SCP_SYNC(c);
+    if (!ok) return 0;
+  }
+  double* z = c.wd + c.g->L.scr;           // n <= pcap <= scr size (see make_layout)
+  for (int sweep = 0; sweep < 3; ++sweep) {
+    // z <- residual rhs - G y  (sweep 0: y = 0 -> rhs)
+    SCP_PHASE(c) {
+      for (int r = tid; r < n; r += c.nthreads) {
+        double acc = rhs[r];
+        if (sweep > 0)
+          for (int q2 = 0; q2 < n; ++q2)
+            acc -= (q2 <= r ? G0[(size_t)q2 * ld + r] : G0[(size_t)r * ld + q2]) * y[q2];
+        z[r] = acc;
+      }
+    }
+    SCP_SYNC(c);
+    for (int j = 0; j < n; ++j) {           // forward  L w = z
+      const double wj = z[j] / A[(size_t)j * ld + j];
+      SCP_SYNC(c);
+      SCP_PHASE(c) {
+        for (int i = j + 1 + tid; i < n; i += c.nthreads) z[i] -= A[(size_t)j * ld + i] * wj;
+        if (tid == 0) z[j] = wj;
+      }
+      SCP_SYNC(c);
+    }
+    for (int j = n - 1; j >= 0; --j) {      // backward L' dy = w
+      const double yj = z[j] / A[(size_t)j * ld + j];
+      SCP_SYNC(c);
+      SCP_PHASE(c) {
+        for (int i = tid; i < j; i += c.nthreads) z[i] -= A[(size_t)i * ld + j] * yj;
+        if (tid == 0) z[j] = yj;
+      }
+      SCP_SYNC(c);
+    }
+    SCP_PHASE(c) { for (int r = tid; r < n; r += c.nthreads) y[r] += z[r]; }
+    SCP_SYNC(c);
+  }
+  return 1;
+}
+
+// One full polish.  Returns 1 when the active set is stable (KKT certificate on the carried
+// rows) and the ADMM state has been replaced by the exact solution; 0 leaves everything untouched.
+SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
+  const int K = c.K, N = c.N, QK = c.Q * K, nch = (K + CH - 1) / CH;
+  const double h = c.g->pb.time_step, ih = 1.0 / h;
+  const PGeom g = make_pgeom(h, K);
+  int* pmark = c.wi + c.g->L.pmark;
+  int* pcmark = c.wi + c.g->L.pcmark;
+  const int* coff = c.wi + c.g->L.coff;
+  const int* cj = c.wi + c.g->L.c_j;
+  const double* ceta = c.wd + c.g->L.c_eta;
+  const double* cb = c.wd + c.g->L.c_bound;
+  double* lam = c.wd + c.g->L.lam;
+  double* plam = c.wd + c.g->L.plam;
+  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+  double *yj = c.wd + c.g->L.yj, *ya = c.wd + c.g->L.ya, *yv = c.wd + c.g->L.yv, *yp = c.wd + c.g->L.yp;
+  double *off = c.wd + c.g->L.off, *deq = c.wd + c.g->L.deq;
+  double *xt = c.wd + c.g->L.xt, *Pt = c.wd + c.g->L.Pt, *w = c.wd + c.g->L.rhs, *FY = c.wd + c.g->L.FY;
+  double* red = c.sm;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  const int use_col = with_collisions && c.ncand > 0;
+  const double ptol = 1e-9, dtol = 1e-9;
+
+  // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0
+  SCP_PHASE(c) {
+    for (int e = tid; e < QK; e += c.nthreads) {
+      int q = e / K, k = e - q * K;
+      double v = va[e];
+      pmark[QK + e] = v > al ? 1 : (v < -al ? -1 : 0);
+      int mj = 0, mv = 0, mp = 0;
+      if (k < K - 1) {
+        v = vj[e]; mj = v > jl ? 1 : (v < -jl ? -1 : 0);
+        double v0q = c.v0[q];
+        v = vv[e]; mv = v > vl - v0q ? 1 : (v < -vl - v0q ? -1 : 0);
+        int a2 = q & 1;
+        v = vp[e]; mp = v > hi[a2] - off[e] ? 1 : (v < lo[a2] - off[e] ? -1 : 0);
+      }
+      pmark[e] = mj; pmark[2 * QK + e] = mv; pmark[3 * QK + e] = mp;
+    }
+    if (use_col)
+      for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+        int k = 1 + t / N, i = t - (k - 1) * N;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx)
+          pcmark[sidx] = lam[((size_t)k * N + i) * N + cj[sidx]] > 0.0;
+      }
+  }
+  SCP_SYNC(c);
+
+  for (int round = 0; round < max_rounds; ++round) {
+    const int n = polish_compact(c);
+    if (n < 0) return 0;
+    if (n > 0 && !polish_solve(c, n, g)) return 0;
+    // scatter multipliers to the dense arrays
+    const double* y = c.wd + c.g->L.py;
+    SCP_PHASE(c) {
+      for (int e = tid; e < QK; e += c.nthreads) { yj[e] = 0; ya[e] = 0; yv[e] = 0; yp[e] = 0; FY[e] = 0; }
+      if (use_col) for (int sidx = tid; sidx < c.ncand; sidx += c.nthreads) plam[sidx] = 0.0;
+    }
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      for (int r = tid; r < n; r += c.nthreads) {
+        PRow a = load_prow(c, r);
+        if (a.type == 0) yj[a.q * K + a.k] = y[r];
+        else if (a.type == 1) ya[a.q * K + a.k] = y[r];
+        else if (a.type == 2) yv[a.q * K + a.k] = y[r];
+        else if (a.type == 3) yp[a.q * K + a.k] = y[r];
+        else {
+          // collision row (lower bound): lam = -y on both owners' entries
+          for (int side = 0; side < 2; ++side) {
+            int own = side ? a.j : a.q, oth = side ? a.q : a.j;
+            for (int sidx = coff[a.k * N + own]; sidx < coff[a.k * N + own + 1]; ++sidx)
+              if (cj[sidx] == oth) plam[sidx] = -y[r];
+          }
+        }
+      }
+    }
+    SCP_SYNC(c);
+    if (use_col) {
+      SCP_PHASE(c) {
+        for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+          int k = 1 + t / N, i = t - (k - 1) * N;
+          double fx = 0, fy = 0;
+          for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) { fx += plam[sidx] * ceta[2 * sidx]; fy += plam[sidx] * ceta[2 * sidx + 1]; }
+          FY[(2 * i) * K + k] = fx; FY[(2 * i + 1) * K + k] = fy;
+        }
+      }
+      SCP_SYNC(c);
+    }
+    transpose_rows(c, 2);                   // w = A'y
+    // x = x_d - 1/2 Pi w ; per agent-axis: cw = C w (two dots), then the update
+    double* cw = c.wd + c.g->L.scr;         // 2 per q
+    SCP_PHASE(c) {
+      for (int q = tid; q < c.Q; q += c.nthreads) {
+        double a0 = 0, a1 = 0;
+        for (int k = 0; k < K; ++k) { double wv = w[q * K + k]; a0 += h * wv; a1 += h * h * ((double)(K - 1 - k) + 0.5) * wv; }
+        // coefficients of C' : H^-1 (d + 1/2 cw)
+        double r0 = deq[2 * q] + 0.5 * a0, r1 = deq[2 * q + 1] + 0.5 * a1;
+        cw[2 * q] = g.i00 * r0 + g.i01 * r1; cw[2 * q + 1] = g.i01 * r0 + g.i11 * r1;
+      }
+    }
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      for (int e = tid; e < QK; e += c.nthreads) {
+        int q = e / K, k = e - q * K;
+        xt[e] = -0.5 * w[e] + h * cw[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * cw[2 * q + 1];
+      }
+    }
+    SCP_SYNC(c);
+    // rows at xt: check violated / wrong-sign, update marks; positions Pt
+    double* s1 = c.wd + c.g->L.scr + 2 * c.Q;
+    double* s2 = s1 + (size_t)c.Q * nch;
+    SCP_PHASE(c) {
+      for (int t = tid; t < c.Q * nch; t += c.nthreads) {
+        int q = t / nch, ch = t - q * nch;
+        int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
+        double a1 = 0, a2 = 0;
+        for (int k = k0; k < k1; ++k) { a1 += xt[q * K + k]; a2 += a1; }
+        s1[t] = a1; s2[t] = a2;
+      }
+    }
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      double changes = 0.0;
+      for (int t = tid; t < c.Q * nch; t += c.nthreads) {
+        int q = t / nch, ch = t - q * nch;
+        int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
+        double c1 = 0, c2 = 0;
+        for (int cc = 0; cc < ch; ++cc) { c2 += s2[q * nch + cc] + (double)CH * c1; c1 += s1[q * nch + cc]; }
+        const double v0q = c.v0[q];
+        const int ax = q & 1;
+        for (int k = k0; k < k1; ++k) {
+          const int e = q * K + k;
+          const double xk = xt[e];
+          c1 += xk; c2 += c1;
+          const double rv_ = h * c1, rp_ = h * h * (c2 - 0.5 * c1);
+          if (k + 1 < K) Pt[q * K + k + 1] = off[e] + rp_;
+          // class, value, lower, upper, multiplier
+          for (int cls = 0; cls < 4; ++cls) {
+            if (cls != 1 && k >= K - 1) continue;
+            double val, lw, up, ym;
+            if (cls == 0) { val = (xt[e + 1] - xk) * ih; lw = -jl; up = jl; ym = yj[e]; }
+            else if (cls == 1) { val = xk; lw = -al; up = al; ym = ya[e]; }
+            else if (cls == 2) { val = rv_; lw = -vl - v0q; up = vl - v0q; ym = yv[e]; }
+            else { val = rp_; lw = lo[ax] - off[e]; up = hi[ax] - off[e]; ym = yp[e]; }
+            int m = pmark[cls * QK + e], nm = m;
+            const double sc = 1.0 + SCP_FMAX(fabs(lw), fabs(up));
+            if (m == 0) { if (val > up + ptol * sc) nm = 1; else if (val < lw - ptol * sc) nm = -1; }
+            else if (m > 0) { if (ym < -dtol) nm = 0; }
+            else { if (ym > dtol) nm = 0; }
+            if (nm != m) { pmark[cls * QK + e] = nm; changes += 1.0; }
+          }
+        }
+        if (ch == 0) Pt[q * K] = c.p0[q];
+      }
+      red[tid] = changes;
+    }
+    SCP_SYNC(c);
+    double changes = reduce_finish(c, 0, 1);
+    if (use_col) {
+      SCP_PHASE(c) {
+        double ch2 = 0.0;
+        for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+          int k = 1 + t / N, i = t - (k - 1) * N;
+          const double pix = Pt[(2 * i) * K + k], piy = Pt[(2 * i + 1) * K + k];
+          for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
+            const int j = cj[sidx];
+            const double gval = ceta[2 * sidx] * (pix - Pt[(2 * j) * K + k]) + ceta[2 * sidx + 1] * (piy - Pt[(2 * j + 1) * K + k]);
+            int m = pcmark[sidx], nm = m;
+            if (!m) { if (gval < cb[sidx] - ptol) nm = 1; }
+            else if (plam[sidx] < -dtol) nm = 0;
+            if (nm != m) { pcmark[sidx] = nm; if (j > i) ch2 += 1.0; }
+          }
+        }
+        red[tid] = ch2;
+      }
+      SCP_SYNC(c);
+      changes += reduce_finish(c, 0, 1);
+    }
+    if (changes == 0.0) {
+      // accept: x, P, and an ADMM state consistent with (x, y): v = bound + y/(rho r) on active rows,
+      // v = row value elsewhere; lam = plam; F = FY (2 lam' - lam with lam' = lam)
+      double* x = c.wd + c.g->L.x;
+      double* P = c.wd + c.g->L.P;
+      double* F = c.wd + c.g->L.F;
+      for (int e2 = 0; e2 < 1; ++e2) {
+        SCP_PHASE(c) { for (int e = tid; e < QK; e += c.nthreads) { x[e] = xt[e]; P[e] = Pt[e]; F[e] = FY[e]; } }
+        SCP_SYNC(c);
+      }
+      forward_rows(c, 0);                   // v := A x, posrow/velrow/P
+      const double rho = c.rho;
+      SCP_PHASE(c) {
+        for (int r = tid; r < n; r += c.nthreads) {
+          PRow a = load_prow(c, r);
+          if (a.type == 4) continue;
+          const int e = a.q * K + a.k;
+          if (a.type == 0) vj[e] += y[r] / (rho * c.g->tb.rj[a.k]);
+          else if (a.type == 1) va[e] += y[r] / (rho * c.g->tb.ra[a.k]);
+          else if (a.type == 2) vv[e] += y[r] / (rho * c.g->tb.rv[a.k]);
+          else vp[e] += y[r] / (rho * c.g->tb.rp[a.k]);
+        }
+        if (use_col)
+          for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+            int k = 1 + t / N, i = t - (k - 1) * N;
+            for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx)
+              lam[((size_t)k * N + i) * N + cj[sidx]] = SCP_FMAX(plam[sidx], 0.0);
+          }
+      }
+      SCP_SYNC(c);
+      return 1;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ ADMM
+struct AdmmOut { int iters; int solved; int certified; double pri, dua; };
+
+SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
+  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
   double* red = c.sm;
   double* x = c.wd + c.g->L.x;
   if (!keep_state) forward_rows(c, 0);
-  const int check = c.g->pb.check_every, maxit = c.g->pb.max_admm_iter;
+  const int check = c.g->pb.check_every;
   for (int it = 1; it <= maxit; ++it) {
     const int chk = (it % check == 0) || it == maxit;
     transpose_rows(c, 0);
@@ -700,7 +1178,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state = 0) {
     double dua = reduce_finish(c, 0, 0);
     double ndua = reduce_finish(c, 1, 0);
     o.pri = pri; o.dua = dua;
-    if (pri <= c.g->pb.eps_abs + c.g->pb.eps_rel * npri && dua <= c.g->pb.eps_abs + c.g->pb.eps_rel * ndua) { o.solved = 1; break; }
+    if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
     if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
     if (c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
       double est = sqrt((pri / SCP_FMAX(npri, 1e-12)) / SCP_FMAX(dua / SCP_FMAX(ndua, 1e-12), 1e-12));
@@ -729,6 +1207,29 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state = 0) {
     }
   }
   return o;
+}
+
+
+// One subproblem: ADMM in stages of decreasing tolerance; after each stage the polish is tried and,
+// when it certifies the active set, the stage loop ends with the exact minimiser.  Without a
+// certificate the result is the plain ADMM iterate at the final tolerance (eps_abs/eps_rel).
+SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
+  AdmmOut tot; tot.iters = 0; tot.solved = 0; tot.certified = 0; tot.pri = tot.dua = INFINITY;
+  const double ea = c.g->pb.eps_abs, er = c.g->pb.eps_rel;
+  int budget = c.g->pb.max_admm_iter;
+  if (!c.g->pb.polish) return admm_run(c, with_collisions, keep_state, ea, er, budget);
+  double f = c.g->pb.polish_first_eps / SCP_FMAX(ea, 1e-12);
+  if (f < 1.0) f = 1.0;
+  for (int stage = 0; stage < 16 && budget > 0; ++stage) {
+    AdmmOut a = admm_run(c, with_collisions, keep_state, ea * f, er * f, budget);
+    keep_state = 1;
+    tot.iters += a.iters; budget -= a.iters; tot.pri = a.pri; tot.dua = a.dua;
+    if (!a.solved) break;
+    if (polish(c, with_collisions, c.g->pb.polish_rounds)) { tot.solved = 1; tot.certified = 1; tot.pri = tot.dua = 0.0; return tot; }
+    if (f <= 1.0) { tot.solved = 1; break; }
+    f = SCP_FMAX(1.0, f * c.g->pb.polish_stage_factor);
+  }
+  return tot;
 }
 
 // ------------------------------------------------------------------ outputs
@@ -765,7 +1266,8 @@ SCP_DEV void solve_scenario(Ctx& c) {
   setup_scenario(c);
   c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0;
   factor_operator(c);
-  AdmmOut a0 = admm_run(c, 0, 0);                       // QP #0, scp.py:138
+  AdmmOut a0 = solve_qp(c, 0, 0);
+  r.polish_ok += a0.certified;                       // QP #0, scp.py:138
   r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
   if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
   forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
@@ -791,7 +1293,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       for (int e = tid; e < c.Q * K; e += c.nthreads) { Pb[e] = P[e]; xprev[e] = x[e]; }
     }
     SCP_SYNC(c);
-    AdmmOut a; a.iters = 0; a.solved = 0; a.pri = a.dua = 0;
+    AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.pri = a.dua = 0;
     mark_near_rows(c, c.g->pb.cand_margin);
     c.rho = c.g->pb.rho0;
     int have_state = 0;
@@ -800,7 +1302,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       build_candidates(c);
       if (c.copies > r.max_copies) r.max_copies = c.copies;
       if (!have_state || c.copies != old_copies) factor_operator(c);
-      a = admm_run(c, 1, have_state);                  // QP #t, scp.py:155
+      a = solve_qp(c, 1, have_state);                  // QP #t, scp.py:155
       have_state = 1;
       r.admm_iterations += a.iters;
       r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;
@@ -810,6 +1312,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       r.rebuilds++;
     }
     if (!a.solved) r.qp_unsolved++;
+    r.polish_ok += a.certified;
     r.pri_res = a.pri; r.dua_res = a.dua;
     // rel step on accelerations, scp.py:157-163
     SCP_PHASE(c) {

@@ -45,6 +45,10 @@ class Problem(C.Structure):
         ("w_col", C.c_double),
         ("cand_margin", C.c_double),
         ("verify_tol", C.c_double),
+        ("polish_first_eps", C.c_double),
+        ("polish_stage_factor", C.c_double),
+        ("polish_rounds", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

@@ -3,6 +3,7 @@
 // exists to debug the solver logic in a container without a GPU.  The product
 // package never builds, loads or falls back to this file.
 #define SCP_EMU 1
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -22,8 +23,8 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
   const double* tb = ht.blob.data();
   g.tb.B1 = tb + ht.oB1; g.tb.B2 = tb + ht.oB2; g.tb.rj = tb + ht.orj; g.tb.ra = tb + ht.ora;
   g.tb.rv = tb + ht.orv; g.tb.rp = tb + ht.orp; g.tb.rc = tb + ht.orc;
-  std::vector<double> wd(g.L.n_double, 0.0);
-  std::vector<int> wi(g.L.n_int, 0);
+  std::vector<double> wd(g.L.n_double, std::nan(""));   // poisoned: the GPU scratch is uninitialised too
+  std::vector<int> wi(g.L.n_int, 0x7f7f7f7f);
   std::vector<double> sm(4 * RED + (size_t)K * K, 0.0);
   for (int b = 0; b < B; ++b) {
     Ctx c;
