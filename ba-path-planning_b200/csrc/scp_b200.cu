@@ -39,7 +39,8 @@ int fail(int code, const std::string& msg) {
 
 constexpr int SOLVE_THREADS = 512;
 constexpr size_t SMEM_BASE = 4 * scp::RED * sizeof(double);
-constexpr size_t SMEM_NMAT_LIMIT = 160 * 1024;
+constexpr size_t SMEM_NMAT_LIMIT = 96 * 1024;
+constexpr size_t SMEM_TOTAL_LIMIT = 227 * 1024;
 
 size_t nmat_smem_bytes(int K) {
   size_t b = (size_t)K * K * sizeof(double);
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
                  const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
                  double* ws_d, int* ws_i, double* acc, double* pos, double* vel, scp_b200_record* rec,
-                 unsigned int* counter, int nmat_in_smem) {
+                 unsigned int* counter, int nmat_in_smem, int hot_in_smem) {
   extern __shared__ double smem[];
   __shared__ int s_b;
   scp::Ctx c;
@@ -78,6 +79,18 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
   c.sm = smem;
   c.nmat = nullptr;
   c.nmat_in_smem = nmat_in_smem;
+  {
+    const size_t QK = (size_t)c.Q * c.K;
+    double* hot = smem + 4 * scp::RED + (nmat_in_smem ? (size_t)c.K * c.K : 0);
+    c.a_x = hot_in_smem ? hot + 0 * QK : c.wd + g.L.x;
+    c.a_rhs = hot_in_smem ? hot + 1 * QK : c.wd + g.L.rhs;
+    c.a_vj = hot_in_smem ? hot + 2 * QK : c.wd + g.L.vj;
+    c.a_va = hot_in_smem ? hot + 3 * QK : c.wd + g.L.va;
+    c.a_vv = hot_in_smem ? hot + 4 * QK : c.wd + g.L.vv;
+    c.a_vp = hot_in_smem ? hot + 5 * QK : c.wd + g.L.vp;
+    c.a_P = hot_in_smem ? hot + 6 * QK : c.wd + g.L.P;
+    c.a_F = hot_in_smem ? hot + 7 * QK : c.wd + g.L.F;
+  }
   for (;;) {
     if (threadIdx.x == 0) s_b = (int)atomicAdd(counter, 1u);
     __syncthreads();
@@ -267,8 +280,10 @@ int scp_b200_default_slots(const scp_b200_problem* prob) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
-  const size_t smem = SMEM_BASE + nmat_smem_bytes(prob->n_steps);
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  size_t smem = SMEM_BASE + nmat_smem_bytes(prob->n_steps);
+  const size_t hot = 8 * (size_t)2 * prob->n_agents * prob->n_steps * sizeof(double);
+  if (smem + hot <= SMEM_TOTAL_LIMIT) smem += hot;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;                        // 4 x 512 threads = the SM's 2048
   size_t slots = (size_t)sms * per_sm;
@@ -300,11 +315,14 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   int* ws_i = (int*)(base + 256 + g.L.n_double * sizeof(double) * (size_t)slots);
   CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
   const size_t nm = nmat_smem_bytes(K);
-  const size_t smem = SMEM_BASE + nm;
+  size_t smem = SMEM_BASE + nm;
+  const size_t hot = 8 * (size_t)2 * prob->n_agents * K * sizeof(double);
+  const int hot_in_smem = (smem + hot <= SMEM_TOTAL_LIMIT) ? 1 : 0;
+  if (hot_in_smem) smem += hot;
   CUDA_OK(cudaFuncSetAttribute(scp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = B < slots ? B : slots;
   scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
-                                                        d_vel, d_records, counter, nm ? 1 : 0);
+                                                        d_vel, d_records, counter, nm ? 1 : 0, hot_in_smem);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -132,6 +132,7 @@ struct Ctx {
   double* sm;                   // shared scratch: [0,4*RED) reductions, then optional Nmat copy
   const double* nmat;           // where P2 reads the operator from (shared or global)
   int nmat_in_smem;
+  double *a_x, *a_rhs, *a_vj, *a_va, *a_vv, *a_vp, *a_P, *a_F;   // hot per-agent-axis arrays: shared memory when they fit
   // per scenario
   const double *p0, *v0, *pf, *vf;
   double *acc, *pos, *vel;
@@ -171,8 +172,8 @@ SCP_DEV void setup_scenario(Ctx& c) {
   const int K = c.K;
   double* off = c.wd + c.g->L.off;
   double* deq = c.wd + c.g->L.deq;
-  double* x = c.wd + c.g->L.x;
-  double* F = c.wd + c.g->L.F;
+  double* x = c.a_x;
+  double* F = c.a_F;
   double* FY = c.wd + c.g->L.FY;
   double* mu = c.wd + c.g->L.mu;
   const double h = c.g->pb.time_step;
@@ -184,6 +185,7 @@ SCP_DEV void setup_scenario(Ctx& c) {
       F[e] = 0.0; FY[e] = 0.0;          // scratch is not zero-initialised by the caller
     }
     for (int t = tid; t < 2 * c.Q; t += c.nthreads) mu[t] = 0.0;
+    for (int t = tid; t <= c.N * K; t += c.nthreads) (c.wi + c.g->L.coff)[t] = 0;
     for (int q = tid; q < c.Q; q += c.nthreads) {
       deq[2 * q + 0] = c.vf[q] - c.v0[q];
       deq[2 * q + 1] = c.pf[q] - (c.p0[q] + h * (double)K * c.v0[q]);
@@ -284,14 +286,14 @@ SCP_DEV void factor_operator(Ctx& c) {
 // mode 0: initialise v := A x (y = 0)            (OSQP warm start with x only, scp.py:443)
 // mode 1: ADMM update v := A x + (v - clip(v))
 // Also writes posrow/velrow and the positions P[q][k], k = 1..K-1 (P[q][0] = p0).
-SCP_DEV void forward_rows(Ctx& c, int mode) {
+SCP_DEV void forward_rows(Ctx& c, int mode, int store_rows = 1) {
   const int K = c.K, nch = (K + CH - 1) / CH;
   const double h = c.g->pb.time_step, ih = 1.0 / h;
-  double* x = c.wd + c.g->L.x;
+  double* x = c.a_x;
   double* s1 = c.wd + c.g->L.scr;            // chunk totals
   double* s2 = s1 + (size_t)c.Q * nch;
-  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
-  double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *P = c.wd + c.g->L.P, *off = c.wd + c.g->L.off;
+  double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
+  double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *P = c.a_P, *off = c.wd + c.g->L.off;
   const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
   const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
   SCP_PHASE(c) {
@@ -310,7 +312,7 @@ SCP_DEV void forward_rows(Ctx& c, int mode) {
       int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
       double c1 = 0, c2 = 0;
       for (int cc = 0; cc < ch; ++cc) { c2 += s2[q * nch + cc] + (double)CH * c1; c1 += s1[q * nch + cc]; }
-      const double v0q = c.v0[q];
+      const double v0q = c.v0[q], p0q = c.p0[q];
       const double lv = -vl - v0q, uv = vl - v0q;
       const int ax = q & 1;
       for (int k = k0; k < k1; ++k) {
@@ -318,8 +320,9 @@ SCP_DEV void forward_rows(Ctx& c, int mode) {
         const double xk = x[e];
         c1 += xk; c2 += c1;
         const double rv_ = h * c1, rp_ = h * h * (c2 - 0.5 * c1);
-        velrow[e] = rv_; posrow[e] = rp_;
-        if (k + 1 < K) P[q * K + k + 1] = off[e] + rp_;
+        const double offe = p0q + h * (double)(k + 1) * v0q;      // == off[e]
+        if (store_rows) { velrow[e] = rv_; posrow[e] = rp_; }
+        if (k + 1 < K) P[q * K + k + 1] = offe + rp_;
         if (mode == 0) {
           va[e] = xk;
           if (k < K - 1) { vj[e] = (x[e + 1] - xk) * ih; vv[e] = rv_; vp[e] = rp_; }
@@ -328,7 +331,7 @@ SCP_DEV void forward_rows(Ctx& c, int mode) {
           if (k < K - 1) {
             v = vj[e]; vj[e] = (x[e + 1] - xk) * ih + (v - clampd(v, -jl, jl));
             v = vv[e]; vv[e] = rv_ + (v - clampd(v, lv, uv));
-            v = vp[e]; vp[e] = rp_ + (v - clampd(v, lo[ax] - off[e], hi[ax] - off[e]));
+            v = vp[e]; vp[e] = rp_ + (v - clampd(v, lo[ax] - offe, hi[ax] - offe));
           }
         }
       }
@@ -347,11 +350,12 @@ SCP_DEV void forward_rows(Ctx& c, int mode) {
 SCP_DEV void transpose_rows(Ctx& c, int mode) {
   const int K = c.K, nch = (K + CH - 1) / CH;
   const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho;
-  double* x = c.wd + c.g->L.x;
-  double* out = c.wd + c.g->L.rhs;
-  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+  double* x = c.a_x;
+  double* out = c.a_rhs;
+  double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
   double *posrow = c.wd + c.g->L.posrow, *off = c.wd + c.g->L.off, *mu = c.wd + c.g->L.mu;
-  double* Fm = c.wd + (mode == 0 ? c.g->L.F : c.g->L.FY);
+  double* Fm = (mode == 0) ? c.a_F : c.wd + c.g->L.FY;
+  const double* Pcur = c.a_P;
   if (mode == 2) { vj = c.wd + c.g->L.yj; va = c.wd + c.g->L.ya; vv = c.wd + c.g->L.yv; vp = c.wd + c.g->L.yp; }
   double* t1 = c.wd + c.g->L.scr;          // chunk totals
   double* t2 = t1 + (size_t)c.Q * nch;
@@ -365,7 +369,7 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
       for (int t = tid; t < c.Q * nch; t += c.nthreads) {
         int q = t / nch, ch = t - q * nch;
         int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
-        const double v0q = c.v0[q];
+        const double v0q = c.v0[q], p0q = c.p0[q];
         const double lv = -vl - v0q, uv = vl - v0q;
         const int ax = q & 1;
         double r1v = 0, r1p = 0, r2p = 0;
@@ -383,10 +387,11 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
           if (k < K - 1) {
             double v = vv[e], z = clampd(v, lv, uv);
             wv = mode == 2 ? v : rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : v - z);
-            v = vp[e]; z = clampd(v, lo[ax] - off[e], hi[ax] - off[e]);
+            const double offe = p0q + h * (double)(k + 1) * v0q;   // == off[e]
+            v = vp[e]; z = clampd(v, lo[ax] - offe, hi[ax] - offe);
             wp = mode == 2 ? v : rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : v - z);
-            // force on position state k+1 <-> row k
-            if (mode == 0) wp += cpr * c.g->tb.rc[k] * posrow[e] + Fm[q * K + k + 1];
+            // force on position state k+1 <-> row k; posrow[e] = P[k+1] - off[e]
+            if (mode == 0) wp += cpr * c.g->tb.rc[k] * (Pcur[q * K + k + 1] - offe) + Fm[q * K + k + 1];
             else wp -= Fm[q * K + k + 1];
           }
           r1v += wv; r1p += wp; r2p += r1p;
@@ -412,8 +417,8 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
 // ------------------------------------------------------------------ x-update
 SCP_DEV void x_update(Ctx& c, int want_mu) {
   const int K = c.K;
-  double* x = c.wd + c.g->L.x;
-  const double* rhs = c.wd + c.g->L.rhs;
+  double* x = c.a_x;
+  const double* rhs = c.a_rhs;
   const double* N0 = c.wd + c.g->L.N0;
   const double* Qm = c.wd + c.g->L.Qm;
   const double* deq = c.wd + c.g->L.deq;
@@ -449,8 +454,8 @@ SCP_DEV void x_update(Ctx& c, int want_mu) {
 // residual of the copy rows when `want_res`.
 SCP_DEV void collision_rows(Ctx& c, int want_res) {
   const int K = c.K, N = c.N;
-  const double* P = c.wd + c.g->L.P;
-  double* F = c.wd + c.g->L.F;
+  const double* P = c.a_P;
+  double* F = c.a_F;
   double* FY = c.wd + c.g->L.FY;
   const int* coff = c.wi + c.g->L.coff;
   const int* cj = c.wi + c.g->L.c_j;
@@ -502,7 +507,7 @@ SCP_DEV void mark_near_rows(Ctx& c, double margin) {
   const double* Pb = c.wd + c.g->L.Pbar;
   unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
   double* lam = c.wd + c.g->L.lam;
-  double* F = c.wd + c.g->L.F;
+  double* F = c.a_F;
   double* FY = c.wd + c.g->L.FY;
   const double R = c.g->pb.min_distance;
   const double r2 = (R + margin) * (R + margin);
@@ -586,7 +591,7 @@ SCP_DEV void build_candidates(Ctx& c) {
 SCP_DEV int verify_rows(Ctx& c, double tol) {
   const int K = c.K, N = c.N;
   const double* Pb = c.wd + c.g->L.Pbar;
-  const double* P = c.wd + c.g->L.P;
+  const double* P = c.a_P;
   unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
   double* lam = c.wd + c.g->L.lam;
   const double R = c.g->pb.min_distance;
@@ -621,7 +626,7 @@ SCP_DEV int verify_rows(Ctx& c, double tol) {
 // min separation and the first row in scan order (k-major, i<j) below R - margin.
 SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, double* first_dist) {
   const int K = c.K, N = c.N;
-  const double* P = c.wd + c.g->L.P;
+  const double* P = c.a_P;
   const double thr = c.g->pb.min_distance - c.g->pb.feas_margin;
   double* red = c.sm;            // slot 0: -min distance ; slot 1: -(first row index) ; slot 2: dist of it
   const long long npairs = (long long)N * (N - 1) / 2;
@@ -729,7 +734,7 @@ SCP_DEV PRow load_prow(Ctx& c, int r) {
 
 // marks: dyn rows pmark[cls*QK + e] in {-1 lower, 0, +1 upper}; collision entries pcmark[s] in {0,1}
 // (only the i<j owner's entry is used).  Returns the number of active rows, or -1 if > cap.
-SCP_DEV int polish_compact(Ctx& c) {
+SCP_DEV int polish_compact(Ctx& c, int use_col) {
   const int K = c.K, N = c.N, QK = c.Q * K;
   const int* pmark = c.wi + c.g->L.pmark;
   const int* pcmark = c.wi + c.g->L.pcmark;
@@ -743,7 +748,7 @@ SCP_DEV int polish_compact(Ctx& c) {
   const double* off = c.wd + c.g->L.off;
   const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
   const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
-  const int total = 4 * QK + (K - 1) * N;           // dyn marks, then one unit per (k,i) owner segment
+  const int total = 4 * QK + (use_col ? (K - 1) * N : 0);   // dyn marks, then one unit per (k,i) owner segment
   const int per = (total + c.nthreads - 1) / c.nthreads;
   int* part = (int*)(c.sm + 2 * RED);
   SCP_PHASE(c) {
@@ -912,15 +917,15 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   const double* cb = c.wd + c.g->L.c_bound;
   double* lam = c.wd + c.g->L.lam;
   double* plam = c.wd + c.g->L.plam;
-  double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+  double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
   double *yj = c.wd + c.g->L.yj, *ya = c.wd + c.g->L.ya, *yv = c.wd + c.g->L.yv, *yp = c.wd + c.g->L.yp;
   double *off = c.wd + c.g->L.off, *deq = c.wd + c.g->L.deq;
-  double *xt = c.wd + c.g->L.xt, *Pt = c.wd + c.g->L.Pt, *w = c.wd + c.g->L.rhs, *FY = c.wd + c.g->L.FY;
+  double *xt = c.wd + c.g->L.xt, *Pt = c.wd + c.g->L.Pt, *w = c.a_rhs, *FY = c.wd + c.g->L.FY;
   double* red = c.sm;
   const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
   const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
   const int use_col = with_collisions && c.ncand > 0;
-  const double ptol = 1e-9, dtol = 1e-9;
+  const double ptol = 1e-9, dtol = 1e-9, etol = 1e-7;
 
   // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0
   SCP_PHASE(c) {
@@ -948,7 +953,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   SCP_SYNC(c);
 
   for (int round = 0; round < max_rounds; ++round) {
-    const int n = polish_compact(c);
+    const int n = polish_compact(c, use_col);
     if (n < 0) return 0;
     if (n > 0 && !polish_solve(c, n, g)) return 0;
     // scatter multipliers to the dense arrays
@@ -1021,7 +1026,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
     }
     SCP_SYNC(c);
     SCP_PHASE(c) {
-      double changes = 0.0;
+      double changes = 0.0, broken = 0.0;
       for (int t = tid; t < c.Q * nch; t += c.nthreads) {
         int q = t / nch, ch = t - q * nch;
         int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
@@ -1046,20 +1051,21 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
             int m = pmark[cls * QK + e], nm = m;
             const double sc = 1.0 + SCP_FMAX(fabs(lw), fabs(up));
             if (m == 0) { if (val > up + ptol * sc) nm = 1; else if (val < lw - ptol * sc) nm = -1; }
-            else if (m > 0) { if (ym < -dtol) nm = 0; }
-            else { if (ym > dtol) nm = 0; }
+            else if (m > 0) { if (ym < -dtol) nm = 0; if (fabs(val - up) > etol * sc) broken += 1.0; }
+            else { if (ym > dtol) nm = 0; if (fabs(val - lw) > etol * sc) broken += 1.0; }
             if (nm != m) { pmark[cls * QK + e] = nm; changes += 1.0; }
           }
         }
         if (ch == 0) Pt[q * K] = c.p0[q];
       }
-      red[tid] = changes;
+      red[tid] = changes; red[RED + tid] = broken;
     }
     SCP_SYNC(c);
     double changes = reduce_finish(c, 0, 1);
+    double broken = reduce_finish(c, 1, 1);
     if (use_col) {
       SCP_PHASE(c) {
-        double ch2 = 0.0;
+        double ch2 = 0.0, br2 = 0.0;
         for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
           int k = 1 + t / N, i = t - (k - 1) * N;
           const double pix = Pt[(2 * i) * K + k], piy = Pt[(2 * i + 1) * K + k];
@@ -1068,21 +1074,26 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
             const double gval = ceta[2 * sidx] * (pix - Pt[(2 * j) * K + k]) + ceta[2 * sidx + 1] * (piy - Pt[(2 * j + 1) * K + k]);
             int m = pcmark[sidx], nm = m;
             if (!m) { if (gval < cb[sidx] - ptol) nm = 1; }
-            else if (plam[sidx] < -dtol) nm = 0;
+            else { if (plam[sidx] < -dtol) nm = 0; if (fabs(gval - cb[sidx]) > etol) br2 += 1.0; }
             if (nm != m) { pcmark[sidx] = nm; if (j > i) ch2 += 1.0; }
           }
         }
-        red[tid] = ch2;
+        red[tid] = ch2; red[RED + tid] = br2;
       }
       SCP_SYNC(c);
       changes += reduce_finish(c, 0, 1);
+      broken += reduce_finish(c, 1, 1);
     }
+#ifdef SCP_EMU_DEBUG
+    fprintf(stderr, "  polish round %d n=%d changes=%g broken=%g\n", round, n, changes, broken);
+#endif
+    if (broken > 0.0) return 0;             // active rows not met as equalities: inconsistent (infeasible) set
     if (changes == 0.0) {
       // accept: x, P, and an ADMM state consistent with (x, y): v = bound + y/(rho r) on active rows,
       // v = row value elsewhere; lam = plam; F = FY (2 lam' - lam with lam' = lam)
-      double* x = c.wd + c.g->L.x;
-      double* P = c.wd + c.g->L.P;
-      double* F = c.wd + c.g->L.F;
+      double* x = c.a_x;
+      double* P = c.a_P;
+      double* F = c.a_F;
       for (int e2 = 0; e2 < 1; ++e2) {
         SCP_PHASE(c) { for (int e = tid; e < QK; e += c.nthreads) { x[e] = xt[e]; P[e] = Pt[e]; F[e] = FY[e]; } }
         SCP_SYNC(c);
@@ -1120,14 +1131,14 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
   AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
   double* red = c.sm;
-  double* x = c.wd + c.g->L.x;
+  double* x = c.a_x;
   if (!keep_state) forward_rows(c, 0);
   const int check = c.g->pb.check_every;
   for (int it = 1; it <= maxit; ++it) {
     const int chk = (it % check == 0) || it == maxit;
     transpose_rows(c, 0);
     x_update(c, chk);
-    forward_rows(c, 1);
+    forward_rows(c, 1, chk);
     double pri_col = 0.0;
     if (with_collisions && c.ncand > 0) {
       collision_rows(c, chk);
@@ -1138,7 +1149,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     // ---- residuals in reference units (OSQP termination test, unscaled)
     const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
     const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
-    double *vj = c.wd + c.g->L.vj, *va = c.wd + c.g->L.va, *vv = c.wd + c.g->L.vv, *vp = c.wd + c.g->L.vp;
+    double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
     double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *off = c.wd + c.g->L.off;
     const double ih = 1.0 / c.g->pb.time_step;
     SCP_PHASE(c) {
@@ -1165,7 +1176,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     double npri = reduce_finish(c, 1, 0);
     pri = SCP_FMAX(pri, pri_col);
     transpose_rows(c, 1);      // rhs <- 2x + A'y + C'mu
-    const double* dres = c.wd + c.g->L.rhs;
+    const double* dres = c.a_rhs;
     SCP_PHASE(c) {
       double du = 0.0, nd = 0.0;
       for (int e = tid; e < c.Q * K; e += c.nthreads) {
@@ -1222,6 +1233,9 @@ SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
   if (f < 1.0) f = 1.0;
   for (int stage = 0; stage < 16 && budget > 0; ++stage) {
     AdmmOut a = admm_run(c, with_collisions, keep_state, ea * f, er * f, budget);
+#ifdef SCP_EMU_DEBUG
+    fprintf(stderr, " stage %d f=%g iters=%d solved=%d pri=%.2e dua=%.2e rho=%.3g copies=%d ncand=%d\n", stage, f, a.iters, a.solved, a.pri, a.dua, c.rho, c.copies, c.ncand);
+#endif
     keep_state = 1;
     tot.iters += a.iters; budget -= a.iters; tot.pri = a.pri; tot.dua = a.dua;
     if (!a.solved) break;
@@ -1236,8 +1250,8 @@ SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
 // scp.py:168-175: positions/velocities for k = 0..K-1 (state k), reference layout (N,K,2).
 SCP_DEV void write_outputs(Ctx& c) {
   const int K = c.K;
-  const double* x = c.wd + c.g->L.x;
-  const double* P = c.wd + c.g->L.P;
+  const double* x = c.a_x;
+  const double* P = c.a_P;
   const double* velrow = c.wd + c.g->L.velrow;
   SCP_PHASE(c) {
     for (int e = tid; e < c.Q * K; e += c.nthreads) {
@@ -1284,9 +1298,9 @@ SCP_DEV void solve_scenario(Ctx& c) {
     if (k == 0) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
   }
   int it = 0, converged = 0;
-  double* x = c.wd + c.g->L.x;
+  double* x = c.a_x;
   double* xprev = c.wd + c.g->L.xprev;
-  double* P = c.wd + c.g->L.P;
+  double* P = c.a_P;
   double* Pb = c.wd + c.g->L.Pbar;
   while (r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
     SCP_PHASE(c) {

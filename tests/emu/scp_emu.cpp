@@ -24,12 +24,15 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
   g.tb.B1 = tb + ht.oB1; g.tb.B2 = tb + ht.oB2; g.tb.rj = tb + ht.orj; g.tb.ra = tb + ht.ora;
   g.tb.rv = tb + ht.orv; g.tb.rp = tb + ht.orp; g.tb.rc = tb + ht.orc;
   std::vector<double> wd(g.L.n_double, std::nan(""));   // poisoned: the GPU scratch is uninitialised too
-  std::vector<int> wi(g.L.n_int, 0x7f7f7f7f);
+  std::vector<int> wi(g.L.n_int);
+  { unsigned st = 12345u; for (auto& v : wi) { st = st * 1664525u + 1013904223u; v = (int)(st >> 4) - (1 << 26); } }   // garbage like GPU scratch
   std::vector<double> sm(4 * RED + (size_t)K * K, 0.0);
   for (int b = 0; b < B; ++b) {
     Ctx c;
     c.nthreads = nthreads; c.N = N; c.K = K; c.Q = 2 * N; c.g = &g;
     c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1;
+    c.a_x = c.wd + g.L.x; c.a_rhs = c.wd + g.L.rhs; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va;
+    c.a_vv = c.wd + g.L.vv; c.a_vp = c.wd + g.L.vp; c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F;
     size_t s2 = (size_t)b * N * 2, s3 = (size_t)b * N * K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;

@@ -207,17 +207,17 @@ def test_initial_velocities_and_public_class(torch_cuda, lib, truth_mode):
     from oracle import scp_oracle
     from path_planning import SCP
 
-    p0 = np.array([[2.0, 2.0], [18.0, 2.5], [10.0, 17.0]])
-    pf = np.array([[17.0, 16.0], [3.0, 15.0], [10.5, 3.0]])
+    p0 = np.array([[4.0, 4.0], [16.0, 5.0], [10.0, 15.0]])
+    pf = np.array([[15.0, 14.0], [5.0, 13.0], [10.5, 4.0]])
     v0 = np.array([[0.3, 0.0], [-0.2, 0.1], [0.0, -0.4]])
     vf = np.array([[0.0, 0.2], [0.0, 0.0], [0.1, 0.0]])
-    s = SCP(n_vehicles=3, time_horizon=12.0, time_step=0.2, min_distance=0.8)
+    s = SCP(n_vehicles=3, time_horizon=14.0, time_step=0.2, min_distance=0.8)
     s.set_initial_states(p0, v0)
     s.set_final_states(pf, vf)
     tr = s.generate_trajectories(max_iterations=15)
     assert set(tr) == {"positions", "velocities", "accelerations"} and tr["positions"].shape == (3, s.K, 2)
     assert tr["positions"].dtype == np.float64 and s.trajectories is tr
-    o = scp_oracle.ScpOracle(3, 12.0, 0.2, 0.8)
+    o = scp_oracle.ScpOracle(3, 14.0, 0.2, 0.8)
     o.set_initial_states(p0, v0)
     o.set_final_states(pf, vf)
     ref = o.generate_trajectories()
