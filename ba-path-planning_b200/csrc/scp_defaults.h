@@ -14,7 +14,7 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->scp_tolerance = 1.5e-2;                                            /* scp.py:52 */
   p->feas_margin = 0.01;                                                /* scp.py:610 */
   p->max_scp_iter = 15;                                                 /* scp.py:131 */
-  p->max_admm_iter = 20000;
+  p->max_admm_iter = 5000;
   p->check_every = 25;
   p->adapt_every = 100;
   p->polish = 1;

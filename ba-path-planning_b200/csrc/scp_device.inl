@@ -43,12 +43,14 @@
 #include "../../include/scp_b200.h"
 
 #ifdef SCP_EMU
+#define SCP_CLOCK() 0LL
 #define SCP_DEV inline
 #define SCP_PHASE(c) for (int tid = 0; tid < (c).nthreads; ++tid)
 #define SCP_SYNC(c) ((void)0)
 #define SCP_FMAX(a, b) ((a) > (b) ? (a) : (b))
 #define SCP_FMIN(a, b) ((a) < (b) ? (a) : (b))
 #else
+#define SCP_CLOCK() clock64()
 #define SCP_DEV __device__ __forceinline__
 #define SCP_PHASE(c) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
 #define SCP_SYNC(c) __syncthreads()
@@ -137,6 +139,7 @@ struct Ctx {
   const double *p0, *v0, *pf, *vf;
   double *acc, *pos, *vel;
   scp_b200_record* rec;
+  long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   // block-uniform solver state
   double rho;
   int copies;
@@ -347,6 +350,7 @@ SCP_DEV void forward_rows(Ctx& c, int mode, int store_rows = 1) {
 // mode 1 (dual residual):        w = rho r (v - clip(v)) = y; wp -= FY; base = 2 x + C'mu
 //   in mode 1 the result is written to rhs and max|.| terms are left to the caller.
 // mode 2 (polish):               w = y read from the dense arrays yj/ya/yv/yp, wp -= FY; base = 0
+// mode 3 (infeasibility test):   w = dy = rho r (A x - clip(v)) (the last multiplier step), wp -= FD; base = 0
 SCP_DEV void transpose_rows(Ctx& c, int mode) {
   const int K = c.K, nch = (K + CH - 1) / CH;
   const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho;
@@ -354,7 +358,9 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
   double* out = c.a_rhs;
   double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
   double *posrow = c.wd + c.g->L.posrow, *off = c.wd + c.g->L.off, *mu = c.wd + c.g->L.mu;
-  double* Fm = (mode == 0) ? c.a_F : c.wd + c.g->L.FY;
+  double* Fm = (mode == 0) ? c.a_F : (mode == 3 ? c.wd + c.g->L.Pt : c.wd + c.g->L.FY);
+  const double* velrow3 = c.wd + c.g->L.velrow;
+  const double* posrow3 = c.wd + c.g->L.posrow;
   const double* Pcur = c.a_P;
   if (mode == 2) { vj = c.wd + c.g->L.yj; va = c.wd + c.g->L.ya; vv = c.wd + c.g->L.yv; vp = c.wd + c.g->L.yp; }
   double* t1 = c.wd + c.g->L.scr;          // chunk totals
@@ -386,10 +392,10 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
           double wv = 0, wp = 0;
           if (k < K - 1) {
             double v = vv[e], z = clampd(v, lv, uv);
-            wv = mode == 2 ? v : rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : v - z);
+            wv = mode == 2 ? v : rho * c.g->tb.rv[k] * (mode == 0 ? 2 * z - v : (mode == 3 ? velrow3[e] - z : v - z));
             const double offe = p0q + h * (double)(k + 1) * v0q;   // == off[e]
             v = vp[e]; z = clampd(v, lo[ax] - offe, hi[ax] - offe);
-            wp = mode == 2 ? v : rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : v - z);
+            wp = mode == 2 ? v : rho * c.g->tb.rp[k] * (mode == 0 ? 2 * z - v : (mode == 3 ? posrow3[e] - z : v - z));
             // force on position state k+1 <-> row k; posrow[e] = P[k+1] - off[e]
             if (mode == 0) wp += cpr * c.g->tb.rc[k] * (Pcur[q * K + k + 1] - offe) + Fm[q * K + k + 1];
             else wp -= Fm[q * K + k + 1];
@@ -397,10 +403,10 @@ SCP_DEV void transpose_rows(Ctx& c, int mode) {
           r1v += wv; r1p += wp; r2p += r1p;
           if (pass == 1) {
             double v = va[e], z = clampd(v, -al, al);
-            double o = mode == 2 ? v : rho * c.g->tb.ra[k] * (mode == 0 ? 2 * z - v : v - z);
+            double o = mode == 2 ? v : rho * c.g->tb.ra[k] * (mode == 0 ? 2 * z - v : (mode == 3 ? x[e] - z : v - z));
             double wj0 = 0, wj1 = 0;   // wj[k-1], wj[k]
-            if (k >= 1) { v = vj[e - 1]; z = clampd(v, -jl, jl); wj0 = mode == 2 ? v : rho * c.g->tb.rj[k - 1] * (mode == 0 ? 2 * z - v : v - z); }
-            if (k < K - 1) { v = vj[e]; z = clampd(v, -jl, jl); wj1 = mode == 2 ? v : rho * c.g->tb.rj[k] * (mode == 0 ? 2 * z - v : v - z); }
+            if (k >= 1) { v = vj[e - 1]; z = clampd(v, -jl, jl); wj0 = mode == 2 ? v : rho * c.g->tb.rj[k - 1] * (mode == 0 ? 2 * z - v : (mode == 3 ? (x[e] - x[e - 1]) * ih - z : v - z)); }
+            if (k < K - 1) { v = vj[e]; z = clampd(v, -jl, jl); wj1 = mode == 2 ? v : rho * c.g->tb.rj[k] * (mode == 0 ? 2 * z - v : (mode == 3 ? (x[e + 1] - x[e]) * ih - z : v - z)); }
             o += (wj0 - wj1) * ih + h * r1v + h * h * (r2p - 0.5 * r1p);
             if (mode == 0) o += sig * x[e];
             else if (mode == 1) o += 2.0 * x[e] + h * mu[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * mu[2 * q + 1];
@@ -462,6 +468,8 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
   const double* ceta = c.wd + c.g->L.c_eta;
   const double* cb = c.wd + c.g->L.c_bound;
   double* lam = c.wd + c.g->L.lam;        // dense [k][i][j]; the two owners keep identical copies
+  double* dlam = c.wd + c.g->L.plam;      // last multiplier step per carried entry (check iterations)
+  double* FD = c.wd + c.g->L.Pt;          // sum_j dlam eta (check iterations; Pt is free outside the polish)
   double* red = c.sm;
   const double rho = c.rho;
   SCP_PHASE(c) {
@@ -470,7 +478,7 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
       int k = 1 + t / N, i = t - (k - 1) * N;
       const double pix = P[(2 * i) * K + k], piy = P[(2 * i + 1) * K + k];
       const double rc = rho * c.g->tb.rc[k - 1];
-      double fx = 0, fy = 0, yx = 0, yy = 0;
+      double fx = 0, fy = 0, yx = 0, yy = 0, dx_ = 0, dy_ = 0;
       for (int s = coff[k * N + i]; s < coff[k * N + i + 1]; ++s) {
         const int j = cj[s];
         const double ex = ceta[2 * s], ey = ceta[2 * s + 1];
@@ -483,9 +491,13 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
         fx += f * ex; fy += f * ey;
         yx += l1 * ex; yy += l1 * ey;
         worst = SCP_FMAX(worst, fabs(l1 - l0) / rc);
+        if (want_res) { dlam[s] = l1 - l0; dx_ += (l1 - l0) * ex; dy_ += (l1 - l0) * ey; }
       }
       F[(2 * i) * K + k] = fx; F[(2 * i + 1) * K + k] = fy;
-      if (want_res) { FY[(2 * i) * K + k] = yx; FY[(2 * i + 1) * K + k] = yy; }
+      if (want_res) {
+        FY[(2 * i) * K + k] = yx; FY[(2 * i + 1) * K + k] = yy;
+        FD[(2 * i) * K + k] = dx_; FD[(2 * i + 1) * K + k] = dy_;
+      }
     }
     if (want_res) red[tid] = worst;
   }
@@ -1124,11 +1136,98 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   return 0;
 }
 
+// ------------------------------------------------------------------ primal infeasibility
+// OSQP's certificate (paper section 3.4) for {C x = d, l <= A x <= u}: the last multiplier step
+// dy (box rows: rho r (A x - z); collision rows: -dlam) together with dmu = -(CC')^-1 C A'dy
+// certifies infeasibility when  ||A'dy + C'dmu||_inf <= eps ||dy||_inf  and
+// u'(dy)+ + l'(dy)- + d'dmu <= -eps ||dy||_inf.  Called at check iterations (rows stored, FD/dlam fresh).
+SCP_DEV int primal_infeasible(Ctx& c, int with_collisions) {
+  const int K = c.K, N = c.N, QK = c.Q * K;
+  const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho;
+  const double eps = 1e-3;   // OSQP's eps_prim_inf default is 1e-4 on its scaled problem; rows here are unscaled
+  const PGeom g = make_pgeom(h, K);
+  double* FD = c.wd + c.g->L.Pt;
+  const int use_col = with_collisions && c.ncand > 0;
+  if (!use_col) { SCP_PHASE(c) { for (int e = tid; e < QK; e += c.nthreads) FD[e] = 0.0; } SCP_SYNC(c); }
+  transpose_rows(c, 3);                       // rhs <- A'dy
+  double* w = c.a_rhs;
+  double* dmu = c.wd + c.g->L.scr;            // 2 per q
+  const double* deq = c.wd + c.g->L.deq;
+  double* red = c.sm;
+  SCP_PHASE(c) {
+    for (int q = tid; q < c.Q; q += c.nthreads) {
+      double a0 = 0, a1 = 0;
+      for (int k = 0; k < K; ++k) { double wv = w[q * K + k]; a0 += h * wv; a1 += h * h * ((double)(K - 1 - k) + 0.5) * wv; }
+      dmu[2 * q] = -(g.i00 * a0 + g.i01 * a1); dmu[2 * q + 1] = -(g.i01 * a0 + g.i11 * a1);
+    }
+  }
+  SCP_SYNC(c);
+  const double *x = c.a_x, *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
+  const double *velrow = c.wd + c.g->L.velrow, *posrow = c.wd + c.g->L.posrow;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  SCP_PHASE(c) {
+    double gn = 0.0, yn = 0.0, sup = 0.0;
+    for (int e = tid; e < QK; e += c.nthreads) {
+      int q = e / K, k = e - q * K;
+      gn = SCP_FMAX(gn, fabs(w[e] + h * dmu[2 * q] + h * h * ((double)(K - 1 - k) + 0.5) * dmu[2 * q + 1]));
+      double z = clampd(va[e], -al, al), dy = rho * c.g->tb.ra[k] * (x[e] - z);
+      yn = SCP_FMAX(yn, fabs(dy)); sup += al * fabs(dy);                   // u dy+ + l dy- with u = -l = al
+      if (k < K - 1) {
+        z = clampd(vj[e], -jl, jl); dy = rho * c.g->tb.rj[k] * ((x[e + 1] - x[e]) * ih - z);
+        yn = SCP_FMAX(yn, fabs(dy)); sup += jl * fabs(dy);
+        const double v0q = c.v0[q], offe = c.p0[q] + h * (double)(k + 1) * v0q;
+        z = clampd(vv[e], -vl - v0q, vl - v0q); dy = rho * c.g->tb.rv[k] * (velrow[e] - z);
+        yn = SCP_FMAX(yn, fabs(dy)); sup += dy > 0 ? (vl - v0q) * dy : (-vl - v0q) * dy;
+        const int a2 = q & 1;
+        z = clampd(vp[e], lo[a2] - offe, hi[a2] - offe); dy = rho * c.g->tb.rp[k] * (posrow[e] - z);
+        yn = SCP_FMAX(yn, fabs(dy)); sup += dy > 0 ? (hi[a2] - offe) * dy : (lo[a2] - offe) * dy;
+      }
+      if (k == 0) sup += deq[2 * q] * dmu[2 * q] + deq[2 * q + 1] * dmu[2 * q + 1];
+    }
+    red[tid] = gn; red[RED + tid] = yn; red[2 * RED + tid] = sup;
+  }
+  SCP_SYNC(c);
+  double gn = reduce_finish(c, 0, 0), yn = reduce_finish(c, 1, 0), sup = reduce_finish(c, 2, 1);
+  if (use_col) {
+    const int* coff = c.wi + c.g->L.coff;
+    const int* cj = c.wi + c.g->L.c_j;
+    const double* ceta = c.wd + c.g->L.c_eta;
+    const double* cb = c.wd + c.g->L.c_bound;
+    const double* dlam = c.wd + c.g->L.plam;
+    SCP_PHASE(c) {
+      double yn2 = 0.0, sup2 = 0.0;
+      for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+        int k = 1 + t / N, i = t - (k - 1) * N;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
+          const int j = cj[sidx];
+          if (j < i) continue;                       // each row once
+          const double dl = dlam[sidx];              // dy = -dl ; u = +inf: only dy <= 0 (dl >= 0) can carry the certificate
+          if (dl <= 0.0) continue;
+          const double offi = ceta[2 * sidx] * ((c.p0[2 * i] + h * k * c.v0[2 * i]) - (c.p0[2 * j] + h * k * c.v0[2 * j])) +
+                              ceta[2 * sidx + 1] * ((c.p0[2 * i + 1] + h * k * c.v0[2 * i + 1]) - (c.p0[2 * j + 1] + h * k * c.v0[2 * j + 1]));
+          yn2 = SCP_FMAX(yn2, dl);
+          sup2 += (cb[sidx] - offi) * (-dl);         // l dy-  (row coordinates)
+        }
+      }
+      red[tid] = yn2; red[RED + tid] = sup2;
+    }
+    SCP_SYNC(c);
+    yn = SCP_FMAX(yn, reduce_finish(c, 0, 0));
+    sup += reduce_finish(c, 1, 1);
+  }
+#ifdef SCP_EMU_DEBUG
+  { static int cnt = 0; if (++cnt % 40 == 0) fprintf(stderr, "   pinf gn=%.3e yn=%.3e sup=%.3e\n", gn, yn, sup); }
+#endif
+  if (!(yn > 1e-10)) return 0;
+  return (gn <= eps * yn) && (sup <= -eps * yn);
+}
+
 // ------------------------------------------------------------------ ADMM
-struct AdmmOut { int iters; int solved; int certified; double pri, dua; };
+struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua; };
 
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
-  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.pri = o.dua = INFINITY;
+  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
   double* red = c.sm;
   double* x = c.a_x;
@@ -1191,6 +1290,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     o.pri = pri; o.dua = dua;
     if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
     if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
+    if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
     if (c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
       double est = sqrt((pri / SCP_FMAX(npri, 1e-12)) / SCP_FMAX(dua / SCP_FMAX(ndua, 1e-12), 1e-12));
       if (est > 5.0 || est < 0.2) {
@@ -1225,21 +1325,28 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
 // when it certifies the active set, the stage loop ends with the exact minimiser.  Without a
 // certificate the result is the plain ADMM iterate at the final tolerance (eps_abs/eps_rel).
 SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
-  AdmmOut tot; tot.iters = 0; tot.solved = 0; tot.certified = 0; tot.pri = tot.dua = INFINITY;
+  AdmmOut tot; tot.iters = 0; tot.solved = 0; tot.certified = 0; tot.infeasible = 0; tot.polish_attempts = 0; tot.pri = tot.dua = INFINITY;
   const double ea = c.g->pb.eps_abs, er = c.g->pb.eps_rel;
   int budget = c.g->pb.max_admm_iter;
-  if (!c.g->pb.polish) return admm_run(c, with_collisions, keep_state, ea, er, budget);
+  if (!c.g->pb.polish) { AdmmOut a = admm_run(c, with_collisions, keep_state, ea, er, budget); a.polish_attempts = 0; return a; }
   double f = c.g->pb.polish_first_eps / SCP_FMAX(ea, 1e-12);
   if (f < 1.0) f = 1.0;
   for (int stage = 0; stage < 16 && budget > 0; ++stage) {
+    long long t0 = SCP_CLOCK();
     AdmmOut a = admm_run(c, with_collisions, keep_state, ea * f, er * f, budget);
+    c.t_admm += SCP_CLOCK() - t0;
 #ifdef SCP_EMU_DEBUG
     fprintf(stderr, " stage %d f=%g iters=%d solved=%d pri=%.2e dua=%.2e rho=%.3g copies=%d ncand=%d\n", stage, f, a.iters, a.solved, a.pri, a.dua, c.rho, c.copies, c.ncand);
 #endif
     keep_state = 1;
     tot.iters += a.iters; budget -= a.iters; tot.pri = a.pri; tot.dua = a.dua;
+    if (a.infeasible) { tot.infeasible = 1; break; }
     if (!a.solved) break;
-    if (polish(c, with_collisions, c.g->pb.polish_rounds)) { tot.solved = 1; tot.certified = 1; tot.pri = tot.dua = 0.0; return tot; }
+    t0 = SCP_CLOCK();
+    const int pol = polish(c, with_collisions, c.g->pb.polish_rounds);
+    c.t_polish += SCP_CLOCK() - t0;
+    tot.polish_attempts++;
+    if (pol) { tot.solved = 1; tot.certified = 1; tot.pri = tot.dua = 0.0; return tot; }
     if (f <= 1.0) { tot.solved = 1; break; }
     f = SCP_FMAX(1.0, f * c.g->pb.polish_stage_factor);
   }
@@ -1271,17 +1378,19 @@ SCP_DEV void solve_scenario(Ctx& c) {
   double* red = c.sm;
   scp_b200_record r;
   r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
-  r.admm_iterations = 0; r.qp_unsolved = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
+  r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
+  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
   r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
   r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
   r.cand_row_iters = 0;
   for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
 
   setup_scenario(c);
-  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0;
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0;
+  const long long t_begin = SCP_CLOCK();
   factor_operator(c);
   AdmmOut a0 = solve_qp(c, 0, 0);
-  r.polish_ok += a0.certified;                       // QP #0, scp.py:138
+  r.polish_ok += a0.certified; r.polish_attempts += a0.polish_attempts;                       // QP #0, scp.py:138
   r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
   if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
   forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
@@ -1307,7 +1416,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       for (int e = tid; e < c.Q * K; e += c.nthreads) { Pb[e] = P[e]; xprev[e] = x[e]; }
     }
     SCP_SYNC(c);
-    AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.pri = a.dua = 0;
+    AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.infeasible = 0; a.pri = a.dua = 0;
     mark_near_rows(c, c.g->pb.cand_margin);
     c.rho = c.g->pb.rho0;
     int have_state = 0;
@@ -1326,7 +1435,9 @@ SCP_DEV void solve_scenario(Ctx& c) {
       r.rebuilds++;
     }
     if (!a.solved) r.qp_unsolved++;
+    r.qp_infeasible += a.infeasible;
     r.polish_ok += a.certified;
+    r.polish_attempts += a.polish_attempts;
     r.pri_res = a.pri; r.dua_res = a.dua;
     // rel step on accelerations, scp.py:157-163
     SCP_PHASE(c) {
@@ -1353,6 +1464,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
   SCP_SYNC(c);
   r.objective = reduce_finish(c, 0, 1);
   write_outputs(c);
+  r.cycles_total = SCP_CLOCK() - t_begin; r.cycles_admm = c.t_admm; r.cycles_polish = c.t_polish;
   SCP_PHASE(c) { if (tid == 0) *c.rec = r; }
   SCP_SYNC(c);
 }

@@ -64,12 +64,17 @@ class Record(C.Structure):
         ("max_copies", C.c_int32),
         ("first_violation", C.c_int32 * 3),
         ("polish_ok", C.c_int32),
+        ("qp_infeasible", C.c_int32),
+        ("polish_attempts", C.c_int32),
         ("first_violation_dist", C.c_double),
         ("min_separation", C.c_double),
         ("objective", C.c_double),
         ("pri_res", C.c_double),
         ("dua_res", C.c_double),
         ("cand_row_iters", C.c_double),
+        ("cycles_total", C.c_int64),
+        ("cycles_admm", C.c_int64),
+        ("cycles_polish", C.c_int64),
         ("rel_step", C.c_double * MAX_SCP_ITER),
     ]
 
@@ -168,7 +173,8 @@ def record_to_dict(r: Record) -> dict:
         status=int(r.status), scp_iterations=int(r.scp_iterations), converged=bool(r.converged),
         initial_feasible=bool(r.initial_feasible), admm_iterations=int(r.admm_iterations),
         qp_unsolved=int(r.qp_unsolved), rebuilds=int(r.rebuilds), max_copies=int(r.max_copies),
-        first_violation=tuple(int(v) for v in r.first_violation), polish_ok=int(r.polish_ok),
+        first_violation=tuple(int(v) for v in r.first_violation), polish_ok=int(r.polish_ok), qp_infeasible=int(r.qp_infeasible), polish_attempts=int(r.polish_attempts),
+        cycles_total=int(r.cycles_total), cycles_admm=int(r.cycles_admm), cycles_polish=int(r.cycles_polish),
         first_violation_dist=float(r.first_violation_dist), min_separation=float(r.min_separation),
         objective=float(r.objective), pri_res=float(r.pri_res), dua_res=float(r.dua_res), cand_row_iters=float(r.cand_row_iters),
         rel_steps=[float(r.rel_step[i]) for i in range(n)],

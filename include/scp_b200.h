@@ -75,11 +75,14 @@ typedef struct scp_b200_record {
   int32_t max_copies;      /* largest per-(agent,step) candidate count */
   int32_t first_violation[3]; /* k,i,j of the gate's first violation, -1 if none */
   int32_t polish_ok;       /* subproblems that ended with a KKT certificate */
+  int32_t qp_infeasible;   /* subproblems stopped by the primal infeasibility certificate (subset of qp_unsolved) */
+  int32_t polish_attempts;
   double first_violation_dist;
   double min_separation;   /* of the returned positions, k in [0,K) */
   double objective;        /* sum ||a||^2 of the returned accelerations */
   double pri_res, dua_res; /* of the last subproblem */
   double cand_row_iters;   /* sum over ADMM iterations of collision rows actually carried */
+  int64_t cycles_total, cycles_admm, cycles_polish; /* SM clock cycles spent on this scenario */
   double rel_step[SCP_B200_MAX_SCP_ITER]; /* scp.py:157-160, one per trip */
 } scp_b200_record;
 
