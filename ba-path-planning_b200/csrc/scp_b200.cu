@@ -90,6 +90,9 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     c.a_vp = hot_in_smem ? hot + 5 * QK : c.wd + g.L.vp;
     c.a_P = hot_in_smem ? hot + 6 * QK : c.wd + g.L.P;
     c.a_F = hot_in_smem ? hot + 7 * QK : c.wd + g.L.F;
+    // warp-fused iteration: needs the operator and the hot arrays in shared memory and K <= 128
+    c.fused_epl = (hot_in_smem && nmat_in_smem && c.K <= 64) ? 2 : 0;
+    c.fused_rows = hot + 8 * QK;
   }
   for (;;) {
     if (threadIdx.x == 0) s_b = (int)atomicAdd(counter, 1u);
@@ -282,7 +285,7 @@ int scp_b200_default_slots(const scp_b200_problem* prob) {
   scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
   size_t smem = SMEM_BASE + nmat_smem_bytes(prob->n_steps);
   const size_t hot = 8 * (size_t)2 * prob->n_agents * prob->n_steps * sizeof(double);
-  if (smem + hot <= SMEM_TOTAL_LIMIT) smem += hot;
+  if (smem + hot + (size_t)(SOLVE_THREADS / 32) * prob->n_steps * sizeof(double) <= SMEM_TOTAL_LIMIT) smem += hot;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;                        // 4 x 512 threads = the SM's 2048
@@ -317,8 +320,11 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   const size_t nm = nmat_smem_bytes(K);
   size_t smem = SMEM_BASE + nm;
   const size_t hot = 8 * (size_t)2 * prob->n_agents * K * sizeof(double);
-  const int hot_in_smem = (smem + hot <= SMEM_TOTAL_LIMIT) ? 1 : 0;
+  const int hot_in_smem = (smem + hot + (size_t)(SOLVE_THREADS / 32) * K * sizeof(double) <= SMEM_TOTAL_LIMIT) ? 1 : 0;
   if (hot_in_smem) smem += hot;
+  const size_t fused_rows = (size_t)(SOLVE_THREADS / 32) * K * sizeof(double);
+  if (hot_in_smem && smem + fused_rows <= SMEM_TOTAL_LIMIT) smem += fused_rows;
+  else if (hot_in_smem) return fail(3, "internal: shared memory plan");
   CUDA_OK(cudaFuncSetAttribute(scp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = B < slots ? B : slots;
   scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,

@@ -139,6 +139,8 @@ struct Ctx {
   const double *p0, *v0, *pf, *vf;
   double *acc, *pos, *vel;
   scp_b200_record* rec;
+  int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
+  double* fused_rows;           // per-warp right-hand-side rows (shared)
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   // block-uniform solver state
   double rho;
@@ -452,6 +454,160 @@ SCP_DEV void x_update(Ctx& c, int want_mu) {
   }
   SCP_SYNC(c);
 }
+
+#ifndef SCP_EMU
+// ------------------------------------------------------------------ fused iteration (GPU only)
+// One ADMM iteration for the agent-axis part with ONE warp per agent-axis q and NO block barrier
+// inside: lanes hold EPL consecutive-by-32 steps (k = lane + 32 e), suffix/prefix sums run as warp
+// shuffles, the K x K operator is applied from shared memory with the right-hand side broadcast from
+// a per-warp shared row.  Same arithmetic as transpose_rows(0) + x_update + forward_rows(1); used for
+// the iterations without a residual check when the hot arrays live in shared memory.
+template <int EPL>
+__device__ __forceinline__ void warp_suffix_sum(double (&v)[EPL], int lane) {
+  // inclusive suffix sum over the sequence k = lane + 32 e (e major): out[k] = sum_{k' >= k} in[k']
+  double carry = 0.0;
+#pragma unroll
+  for (int e = EPL - 1; e >= 0; --e) {
+    double s = v[e];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double o = __shfl_down_sync(0xffffffffu, s, d);
+      if (lane + d < 32) s += o;
+    }
+    s += carry;
+    v[e] = s;
+    carry = __shfl_sync(0xffffffffu, s, 0);
+  }
+}
+
+template <int EPL>
+__device__ __forceinline__ void warp_prefix_sum(double (&v)[EPL], int lane) {
+  double carry = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    double s = v[e];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double o = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += o;
+    }
+    s += carry;
+    v[e] = s;
+    carry = __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+
+template <int EPL>
+__device__ __forceinline__ void admm_iter_fused(Ctx& c, double* rhs_rows /* nwarps x K in shared */) {
+  const int K = c.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho, sig = c.g->pb.sigma;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double cpr = (double)c.copies * rho;
+  const double* Nm = c.nmat;
+  const double* N0 = c.wd + c.g->L.N0;
+  const double* deq = c.wd + c.g->L.deq;
+  double* myrhs = rhs_rows + warp * K;
+  double trj[EPL], tra[EPL], trv[EPL], trp[EPL], trc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int k = lane + 32 * e;
+    const bool in = k < K;
+    trj[e] = in ? rho * c.g->tb.rj[k] : 0.0; tra[e] = in ? rho * c.g->tb.ra[k] : 0.0;
+    trv[e] = in ? rho * c.g->tb.rv[k] : 0.0; trp[e] = in ? rho * c.g->tb.rp[k] : 0.0;
+    trc[e] = in ? cpr * c.g->tb.rc[k] : 0.0;
+  }
+  for (int q = warp; q < c.Q; q += nwarps) {
+    const double v0q = c.v0[q], p0q = c.p0[q];
+    const double lv = -vl - v0q, uv = vl - v0q;
+    const double plo = c.g->pb.space[q & 1], phi = c.g->pb.space[2 + (q & 1)];
+    double *x = c.a_x + q * K, *vj = c.a_vj + q * K, *va = c.a_va + q * K, *vv = c.a_vv + q * K, *vp = c.a_vp + q * K;
+    double *P = c.a_P + q * K, *F = c.a_F + q * K;
+    double xo[EPL], sj[EPL], sa[EPL], sv[EPL], sp[EPL], wj[EPL], wv[EPL], wp[EPL], wa[EPL], off[EPL];
+    // ---- rows -> weighted reflections
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int k = lane + 32 * e;
+      xo[e] = 0; sj[e] = sa[e] = sv[e] = sp[e] = 0; wj[e] = wv[e] = wp[e] = wa[e] = 0; off[e] = 0;
+      if (k < K) {
+        xo[e] = x[k];
+        double v = va[k], z = clampd(v, -al, al);
+        sa[e] = v - z; wa[e] = tra[e] * (2 * z - v);
+        if (k < K - 1) {
+          v = vj[k]; z = clampd(v, -jl, jl); sj[e] = v - z; wj[e] = trj[e] * (2 * z - v);
+          v = vv[k]; z = clampd(v, lv, uv); sv[e] = v - z; wv[e] = trv[e] * (2 * z - v);
+          off[e] = p0q + h * (double)(k + 1) * v0q;
+          v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - z;
+          wp[e] = trp[e] * (2 * z - v) + trc[e] * (P[k + 1] - off[e]) + F[k + 1];
+        }
+      }
+    }
+    // ---- transpose: D'wj + wa + V'wv + S'wp
+    double r1v[EPL], r1p[EPL], r2p[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { r1v[e] = wv[e]; r1p[e] = wp[e]; }
+    warp_suffix_sum<EPL>(r1v, lane);
+    warp_suffix_sum<EPL>(r1p, lane);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) r2p[e] = r1p[e];
+    warp_suffix_sum<EPL>(r2p, lane);
+    double last = 0.0;   // wj[k-1] across the lane/element boundary
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int k = lane + 32 * e;
+      double prev = __shfl_up_sync(0xffffffffu, wj[e], 1);
+      if (lane == 0) prev = last;                    // element 32e - 1 lives in lane 31 of the previous element row
+      last = __shfl_sync(0xffffffffu, wj[e], 31);
+      if (k < K)
+        myrhs[k] = sig * xo[e] + (prev - wj[e]) * ih + wa[e] + h * r1v[e] + h * h * (r2p[e] - 0.5 * r1p[e]);
+    }
+    __syncwarp();
+    // ---- x = Nmat rhs + N0 d
+    double xn[EPL];
+    const double d0 = deq[2 * q], d1 = deq[2 * q + 1];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int k = lane + 32 * e;
+      xn[e] = (k < K) ? N0[2 * k] * d0 + N0[2 * k + 1] * d1 : 0.0;
+    }
+    for (int j = 0; j < K; ++j) {
+      const double r = myrhs[j];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = lane + 32 * e;
+        if (k < K) xn[e] += Nm[j * K + k] * r;
+      }
+    }
+    __syncwarp();
+    // ---- forward rows and v update
+    double c1[EPL], c2[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) c1[e] = xn[e];
+    warp_prefix_sum<EPL>(c1, lane);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) c2[e] = c1[e];
+    warp_prefix_sum<EPL>(c2, lane);
+    double first_next = 0.0;   // x[k+1] across the boundary: element row e+1, lane 0
+#pragma unroll
+    for (int e = EPL - 1; e >= 0; --e) {
+      const int k = lane + 32 * e;
+      double nxt = __shfl_down_sync(0xffffffffu, xn[e], 1);
+      if (lane == 31) nxt = first_next;
+      first_next = __shfl_sync(0xffffffffu, xn[e], 0);
+      if (k < K) {
+        x[k] = xn[e];
+        va[k] = xn[e] + sa[e];
+        if (k < K - 1) {
+          const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
+          vj[k] = (nxt - xn[e]) * ih + sj[e];
+          vv[k] = rv_ + sv[e];
+          vp[k] = rp_ + sp[e];
+          P[k + 1] = off[e] + rp_;
+        }
+      }
+    }
+  }
+}
+#endif
 
 // ------------------------------------------------------------------ collision rows
 // One thread per (k, i), k = 1..K-1: walks its candidate rows, updates the row
@@ -1235,9 +1391,17 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
   const int check = c.g->pb.check_every;
   for (int it = 1; it <= maxit; ++it) {
     const int chk = (it % check == 0) || it == maxit;
-    transpose_rows(c, 0);
-    x_update(c, chk);
-    forward_rows(c, 1, chk);
+#ifndef SCP_EMU
+    if (!chk && c.fused_epl > 0) {
+      admm_iter_fused<2>(c, c.fused_rows);
+      __syncthreads();
+    } else
+#endif
+    {
+      transpose_rows(c, 0);
+      x_update(c, chk);
+      forward_rows(c, 1, chk);
+    }
     double pri_col = 0.0;
     if (with_collisions && c.ncand > 0) {
       collision_rows(c, chk);

@@ -30,7 +30,7 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
   for (int b = 0; b < B; ++b) {
     Ctx c;
     c.nthreads = nthreads; c.N = N; c.K = K; c.Q = 2 * N; c.g = &g;
-    c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1;
+    c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1; c.fused_epl = 0; c.fused_rows = nullptr;
     c.a_x = c.wd + g.L.x; c.a_rhs = c.wd + g.L.rhs; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va;
     c.a_vv = c.wd + g.L.vv; c.a_vp = c.wd + g.L.vp; c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F;
     size_t s2 = (size_t)b * N * 2, s3 = (size_t)b * N * K * 2;
