@@ -23,9 +23,9 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->w_jerk = 0.4; p->w_acc = 2.0; p->w_vel = 10.0; p->w_pos = 1.0; p->w_col = 4.0;
   p->cand_margin = 0.5;
   p->verify_tol = 1e-6;
-  p->polish_first_eps = 1e-1;
+  p->polish_first_eps = 5e-2;
   p->polish_stage_factor = 0.3;
-  p->polish_rounds = 12;
+  p->polish_rounds = 40;
   p->reserved0 = 0;
 }
 #endif

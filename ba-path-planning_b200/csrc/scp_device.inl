@@ -78,7 +78,8 @@ struct Layout {
   size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
   size_t c_eta, c_bound, lam, scr, red, n_double;
   size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey;   // polish (doubles)
-  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn;                       // polish (ints)
+  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec;          // polish (ints)
+  size_t pscore, pcscore;                                               // polish (doubles)
   int pcap;
   size_t cnt, coff, c_j, flags, n_int;
   size_t cap;
@@ -102,18 +103,19 @@ Layout make_layout(int N, int K) {
   L.off = take(QK); L.deq = take(2 * Q); L.mu = take(2 * Q);
   L.cap = (size_t)N * (size_t)K * (size_t)(N > 1 ? N - 1 : 1);
   L.c_eta = take(2 * L.cap); L.c_bound = take(L.cap); L.lam = take((size_t)N * N * K);
-  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 2 * Q + 1600);
+  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 2 * Q + 2100);
   L.red = take(4 * RED);
-  L.pcap = 12 * N + 128; if (L.pcap > 1536) L.pcap = 1536;
+  L.pcap = 12 * N + 128; if (L.pcap > 1024) L.pcap = 1024;
   L.xt = take(QK); L.Pt = take(QK); L.yj = take(QK); L.ya = take(QK); L.yv = take(QK); L.yp = take(QK);
   L.plam = take(L.cap);
   L.pL = take((size_t)L.pcap * L.pcap); L.pG = take((size_t)L.pcap * L.pcap); L.prhs = take(L.pcap); L.py = take(L.pcap); L.pb_ = take(L.pcap);
   L.pex = take(L.pcap); L.pey = take(L.pcap);
+  L.pscore = take(4 * QK); L.pcscore = take(L.cap);
   L.n_double = o;
   size_t p = 0;
   auto takei = [&](size_t n) { size_t r = p; p += (n + 3) & ~(size_t)3; return r; };
   L.cnt = takei((size_t)N * K + 1); L.coff = takei((size_t)N * K + 1); L.c_j = takei(L.cap); L.flags = takei(((size_t)N * N * K + 3) / 4);
-  L.pmark = takei(4 * QK); L.pcmark = takei(L.cap);
+  L.pmark = takei(4 * QK); L.pcmark = takei(L.cap); L.pdec = takei(4 * QK); L.pcdec = takei(L.cap);
   L.ptype = takei(L.pcap); L.pq = takei(L.pcap); L.pj2 = takei(L.pcap); L.pk = takei(L.pcap); L.psgn = takei(L.pcap);
   L.n_int = p;
   return L;
@@ -971,13 +973,14 @@ SCP_DEV int polish_compact(Ctx& c, int use_col) {
   return ntot;
 }
 
-// Cholesky solve of (G + delta I) y = rhs with two refinement sweeps on G.  Returns 0 on breakdown.
+// Solve (G + delta I) y = rhs through an explicit inverse, with two refinement sweeps on G.  Returns 0 on breakdown.
 SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
   const int ld = c.g->L.pcap;
   double* A = c.wd + c.g->L.pL;           // column-major lower triangle: A[col*ld + row]
   double* G0 = c.wd + c.g->L.pG;          // untouched copy of G for the refinement residual
   double* rhs = c.wd + c.g->L.prhs;
   double* y = c.wd + c.g->L.py;
+  double* rhs2 = c.wd + c.g->L.scr + c.g->L.pcap;
   const double* pb = c.wd + c.g->L.pb_;
   const double* deq = c.wd + c.g->L.deq;
   double* red = c.sm;
@@ -1013,30 +1016,43 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
   }
   SCP_SYNC(c);
   const double delta = 1e-11 * SCP_FMAX(reduce_finish(c, 0, 0), 1e-300);
+  // A <- (G + delta I)^-1 by in-place Gauss-Jordan on the full symmetric matrix: every pivot is one fully
+  // parallel n x n update between two barriers (no sequential substitutions).  SPD => no pivoting.
+  double* colb = c.sm;                      // n <= pcap <= RED
+  double* rowb = c.sm + RED;
+  SCP_PHASE(c) {
+    for (int e = tid; e < n * n; e += c.nthreads) {
+      int col = e / n, row = e - col * n;
+      if (row < col) A[(size_t)col * ld + row] = G0[(size_t)row * ld + col];
+      else if (row == col) A[(size_t)col * ld + row] += delta;
+    }
+  }
+  SCP_SYNC(c);
   int ok = 1;
-  for (int j = 0; j < n; ++j) {
+  for (int p = 0; p < n; ++p) {
     SCP_PHASE(c) {
-      for (int i = j + tid; i < n; i += c.nthreads) {
-        double sacc = A[(size_t)j * ld + i] + (i == j ? delta : 0.0);
-        for (int k = 0; k < j; ++k) sacc -= A[(size_t)k * ld + i] * A[(size_t)k * ld + j];
-        A[(size_t)j * ld + i] = sacc;
-      }
+      for (int e = tid; e < n; e += c.nthreads) { colb[e] = A[(size_t)p * ld + e]; rowb[e] = A[(size_t)e * ld + p]; }
     }
     SCP_SYNC(c);
-    const double piv = A[(size_t)j * ld + j];
-    if (!(piv > 0.0)) { ok = 0; }
-    const double d = ok ? sqrt(piv) : 1.0;
-    SCP_SYNC(c);
+    const double piv = colb[p];
+    if (!(piv > 0.0)) ok = 0;
+    const double ip = ok ? 1.0 / piv : 0.0;
     SCP_PHASE(c) {
-      for (int i = j + 1 + tid; i < n; i += c.nthreads) A[(size_t)j * ld + i] /= d;
-      if (tid == 0) A[(size_t)j * ld + j] = d;
+      for (int e = tid; e < n * n; e += c.nthreads) {
+        int col = e / n, row = e - col * n;
+        double v;
+        if (row == p) v = (col == p) ? ip : rowb[col] * ip;
+        else if (col == p) v = -colb[row] * ip;
+        else v = A[(size_t)col * ld + row] - colb[row] * rowb[col] * ip;
+        A[(size_t)col * ld + row] = v;
+      }
     }
     SCP_SYNC(c);
     if (!ok) return 0;
   }
+  // y = Ainv rhs, then two refinement sweeps on the unregularised G
   double* z = c.wd + c.g->L.scr;           // n <= pcap <= scr size (see make_layout)
   for (int sweep = 0; sweep < 3; ++sweep) {
-    // z <- residual rhs - G y  (sweep 0: y = 0 -> rhs)
     SCP_PHASE(c) {
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = rhs[r];
@@ -1047,25 +1063,15 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
       }
     }
     SCP_SYNC(c);
-    for (int j = 0; j < n; ++j) {           // forward  L w = z
-      const double wj = z[j] / A[(size_t)j * ld + j];
-      SCP_SYNC(c);
-      SCP_PHASE(c) {
-        for (int i = j + 1 + tid; i < n; i += c.nthreads) z[i] -= A[(size_t)j * ld + i] * wj;
-        if (tid == 0) z[j] = wj;
+    SCP_PHASE(c) {
+      for (int r = tid; r < n; r += c.nthreads) {
+        double acc = 0.0;
+        for (int q2 = 0; q2 < n; ++q2) acc += A[(size_t)q2 * ld + r] * z[q2];
+        rhs2[r] = acc;
       }
-      SCP_SYNC(c);
     }
-    for (int j = n - 1; j >= 0; --j) {      // backward L' dy = w
-      const double yj = z[j] / A[(size_t)j * ld + j];
-      SCP_SYNC(c);
-      SCP_PHASE(c) {
-        for (int i = tid; i < j; i += c.nthreads) z[i] -= A[(size_t)i * ld + j] * yj;
-        if (tid == 0) z[j] = yj;
-      }
-      SCP_SYNC(c);
-    }
-    SCP_PHASE(c) { for (int r = tid; r < n; r += c.nthreads) y[r] += z[r]; }
+    SCP_SYNC(c);
+    SCP_PHASE(c) { for (int r = tid; r < n; r += c.nthreads) y[r] += rhs2[r]; }
     SCP_SYNC(c);
   }
   return 1;
@@ -1079,6 +1085,12 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   const PGeom g = make_pgeom(h, K);
   int* pmark = c.wi + c.g->L.pmark;
   int* pcmark = c.wi + c.g->L.pcmark;
+  int* pdec = c.wi + c.g->L.pdec;
+  int* pcdec = c.wi + c.g->L.pcdec;
+  double* pscore = c.wd + c.g->L.pscore;
+  double* pcscore = c.wd + c.g->L.pcscore;
+  double* sc3 = c.wd + c.g->L.red;          // one more reduction column (global scratch)
+  const int full_rounds = 6;
   const int* coff = c.wi + c.g->L.coff;
   const int* cj = c.wi + c.g->L.c_j;
   const double* ceta = c.wd + c.g->L.c_eta;
@@ -1194,7 +1206,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
     }
     SCP_SYNC(c);
     SCP_PHASE(c) {
-      double changes = 0.0, broken = 0.0;
+      double changes = 0.0, broken = 0.0, madd = 0.0, mdrop = 0.0;
       for (int t = tid; t < c.Q * nch; t += c.nthreads) {
         int q = t / nch, ch = t - q * nch;
         int k0 = ch * CH, k1 = k0 + CH < K ? k0 + CH : K;
@@ -1218,22 +1230,31 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
             else { val = rp_; lw = lo[ax] - off[e]; up = hi[ax] - off[e]; ym = yp[e]; }
             int m = pmark[cls * QK + e], nm = m;
             const double sc = 1.0 + SCP_FMAX(fabs(lw), fabs(up));
-            if (m == 0) { if (val > up + ptol * sc) nm = 1; else if (val < lw - ptol * sc) nm = -1; }
-            else if (m > 0) { if (ym < -dtol) nm = 0; if (fabs(val - up) > etol * sc) broken += 1.0; }
-            else { if (ym > dtol) nm = 0; if (fabs(val - lw) > etol * sc) broken += 1.0; }
-            if (nm != m) { pmark[cls * QK + e] = nm; changes += 1.0; }
+            double score = 0.0;
+            if (m == 0) {
+              if (val > up + ptol * sc) { nm = 1; score = (val - up) / sc; }
+              else if (val < lw - ptol * sc) { nm = -1; score = (lw - val) / sc; }
+            } else if (m > 0) { if (ym < -dtol) { nm = 0; score = -ym; } if (fabs(val - up) > etol * sc) broken += 1.0; }
+            else { if (ym > dtol) { nm = 0; score = ym; } if (fabs(val - lw) > etol * sc) broken += 1.0; }
+            pdec[cls * QK + e] = nm; pscore[cls * QK + e] = score;
+            if (nm != m) { changes += 1.0; if (nm != 0) madd = SCP_FMAX(madd, score); else mdrop = SCP_FMAX(mdrop, score); }
           }
         }
         if (ch == 0) Pt[q * K] = c.p0[q];
       }
-      red[tid] = changes; red[RED + tid] = broken;
+      red[tid] = changes; red[RED + tid] = broken; red[2 * RED + tid] = madd;
+      sc3[tid] = mdrop;
     }
     SCP_SYNC(c);
     double changes = reduce_finish(c, 0, 1);
     double broken = reduce_finish(c, 1, 1);
+    double madd = reduce_finish(c, 2, 0);
+    SCP_PHASE(c) { red[tid] = sc3[tid]; }
+    SCP_SYNC(c);
+    double mdrop = reduce_finish(c, 0, 0);
     if (use_col) {
       SCP_PHASE(c) {
-        double ch2 = 0.0, br2 = 0.0;
+        double ch2 = 0.0, br2 = 0.0, ma2 = 0.0, md2 = 0.0;
         for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
           int k = 1 + t / N, i = t - (k - 1) * N;
           const double pix = Pt[(2 * i) * K + k], piy = Pt[(2 * i + 1) * K + k];
@@ -1241,21 +1262,45 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
             const int j = cj[sidx];
             const double gval = ceta[2 * sidx] * (pix - Pt[(2 * j) * K + k]) + ceta[2 * sidx + 1] * (piy - Pt[(2 * j + 1) * K + k]);
             int m = pcmark[sidx], nm = m;
-            if (!m) { if (gval < cb[sidx] - ptol) nm = 1; }
-            else { if (plam[sidx] < -dtol) nm = 0; if (fabs(gval - cb[sidx]) > etol) br2 += 1.0; }
-            if (nm != m) { pcmark[sidx] = nm; if (j > i) ch2 += 1.0; }
+            double score = 0.0;
+            if (!m) { if (gval < cb[sidx] - ptol) { nm = 1; score = cb[sidx] - gval; } }
+            else { if (plam[sidx] < -dtol) { nm = 0; score = -plam[sidx]; } if (fabs(gval - cb[sidx]) > etol) br2 += 1.0; }
+            pcdec[sidx] = nm; pcscore[sidx] = score;
+            if (nm != m) { if (j > i) ch2 += 1.0; if (nm) ma2 = SCP_FMAX(ma2, score); else md2 = SCP_FMAX(md2, score); }
           }
         }
-        red[tid] = ch2; red[RED + tid] = br2;
+        red[tid] = ch2; red[RED + tid] = br2; red[2 * RED + tid] = ma2; sc3[tid] = md2;
       }
       SCP_SYNC(c);
       changes += reduce_finish(c, 0, 1);
       broken += reduce_finish(c, 1, 1);
+      madd = SCP_FMAX(madd, reduce_finish(c, 2, 0));
+      SCP_PHASE(c) { red[tid] = sc3[tid]; }
+      SCP_SYNC(c);
+      mdrop = SCP_FMAX(mdrop, reduce_finish(c, 0, 0));
     }
 #ifdef SCP_EMU_DEBUG
     fprintf(stderr, "  polish round %d n=%d changes=%g broken=%g\n", round, n, changes, broken);
 #endif
     if (broken > 0.0) return 0;             // active rows not met as equalities: inconsistent (infeasible) set
+    if (changes > 0.0) {
+      // apply the decisions: all of them in the first rounds (primal-dual active set step); afterwards only the
+      // worst violated row and the worst wrong-sign multiplier per round, which breaks the cycles the full step can enter
+      const int careful = round >= full_rounds;
+      const double ta = careful ? madd * (1.0 - 1e-12) : 0.0, td = careful ? mdrop * (1.0 - 1e-12) : 0.0;
+      SCP_PHASE(c) {
+        for (int u = tid; u < 4 * QK; u += c.nthreads) {
+          const int m = pmark[u], nm = pdec[u];
+          if (nm != m && pscore[u] >= (nm != 0 ? ta : td)) pmark[u] = nm;
+        }
+        if (use_col)
+          for (int sidx = tid; sidx < c.ncand; sidx += c.nthreads) {
+            const int m = pcmark[sidx], nm = pcdec[sidx];
+            if (nm != m && pcscore[sidx] >= (nm != 0 ? ta : td)) pcmark[sidx] = nm;
+          }
+      }
+      SCP_SYNC(c);
+    }
     if (changes == 0.0) {
       // accept: x, P, and an ADMM state consistent with (x, y): v = bound + y/(rho r) on active rows,
       // v = row value elsewhere; lam = plam; F = FY (2 lam' - lam with lam' = lam)
@@ -1379,16 +1424,64 @@ SCP_DEV int primal_infeasible(Ctx& c, int with_collisions) {
   return (gn <= eps * yn) && (sup <= -eps * yn);
 }
 
+// Signature (count, weighted id sum) of the rows the ADMM state currently marks active: box rows with
+// v outside the box (y != 0), collision rows with lam > 0.  Two equal signatures at consecutive
+// residual checks = the active set has settled -> worth a polish attempt.
+SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double* idsum) {
+  const int K = c.K, N = c.N, QK = c.Q * K;
+  const double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  const double h = c.g->pb.time_step;
+  double* red = c.sm;
+  SCP_PHASE(c) {
+    double n = 0.0, sidsum = 0.0;
+    for (int e = tid; e < QK; e += c.nthreads) {
+      int q = e / K, k = e - q * K;
+      double v = va[e];
+      int m = (v > al) ? 2 : ((v < -al) ? 1 : 0);
+      if (m) { n += 1.0; sidsum += (double)((4 * e + 0) * 3 + m); }
+      if (k < K - 1) {
+        v = vj[e]; m = (v > jl) ? 2 : ((v < -jl) ? 1 : 0);
+        if (m) { n += 1.0; sidsum += (double)((4 * e + 1) * 3 + m); }
+        const double v0q = c.v0[q], offe = c.p0[q] + h * (double)(k + 1) * v0q;
+        v = vv[e]; m = (v > vl - v0q) ? 2 : ((v < -vl - v0q) ? 1 : 0);
+        if (m) { n += 1.0; sidsum += (double)((4 * e + 2) * 3 + m); }
+        const int a2 = q & 1;
+        v = vp[e]; m = (v > hi[a2] - offe) ? 2 : ((v < lo[a2] - offe) ? 1 : 0);
+        if (m) { n += 1.0; sidsum += (double)((4 * e + 3) * 3 + m); }
+      }
+    }
+    if (with_collisions && c.ncand > 0) {
+      const int* coff = c.wi + c.g->L.coff;
+      const int* cj = c.wi + c.g->L.c_j;
+      const double* lam = c.wd + c.g->L.lam;
+      for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
+        int k = 1 + t / N, i = t - (k - 1) * N;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
+          const int j = cj[sidx];
+          if (j > i && lam[((size_t)k * N + i) * N + j] > 0.0) { n += 1.0; sidsum += (double)(12 * QK + (k * N + i) * N + j); }
+        }
+      }
+    }
+    red[tid] = n; red[RED + tid] = sidsum;
+  }
+  SCP_SYNC(c);
+  *count = reduce_finish(c, 0, 1);
+  *idsum = reduce_finish(c, 1, 1);
+}
+
 // ------------------------------------------------------------------ ADMM
 struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua; };
 
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
-  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.pri = o.dua = INFINITY;
+  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
   double* red = c.sm;
   double* x = c.a_x;
   if (!keep_state) forward_rows(c, 0);
   const int check = c.g->pb.check_every;
+  double prev_sc = -1.0, prev_ss = -1.0, fail_sc = -2.0, fail_ss = -2.0;
   for (int it = 1; it <= maxit; ++it) {
     const int chk = (it % check == 0) || it == maxit;
 #ifndef SCP_EMU
@@ -1455,6 +1548,23 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
     if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
     if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
+    if (c.g->pb.polish) {
+      // polish when the active set has not changed between two consecutive checks (and differs from the
+      // last set that failed), once the iterate is inside a loose residual gate
+      double sc, ss;
+      active_signature(c, with_collisions, &sc, &ss);
+      const double gate = c.g->pb.polish_first_eps;
+      const int settled = (sc == prev_sc && ss == prev_ss) && !(sc == fail_sc && ss == fail_ss);
+      prev_sc = sc; prev_ss = ss;
+      if (settled && pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua)) {
+        const long long t0 = SCP_CLOCK();
+        const int pol = polish(c, with_collisions, c.g->pb.polish_rounds);
+        c.t_polish += SCP_CLOCK() - t0;
+        o.polish_attempts++;
+        if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; break; }
+        fail_sc = sc; fail_ss = ss;
+      }
+    }
     if (c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
       double est = sqrt((pri / SCP_FMAX(npri, 1e-12)) / SCP_FMAX(dua / SCP_FMAX(ndua, 1e-12), 1e-12));
       if (est > 5.0 || est < 0.2) {
@@ -1485,36 +1595,14 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
 }
 
 
-// One subproblem: ADMM in stages of decreasing tolerance; after each stage the polish is tried and,
-// when it certifies the active set, the stage loop ends with the exact minimiser.  Without a
-// certificate the result is the plain ADMM iterate at the final tolerance (eps_abs/eps_rel).
+// One subproblem: a single ADMM run to the final tolerance; the polish is attempted from inside the
+// run whenever the active set has settled, and ends it with the exact minimiser when it certifies.
 SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
-  AdmmOut tot; tot.iters = 0; tot.solved = 0; tot.certified = 0; tot.infeasible = 0; tot.polish_attempts = 0; tot.pri = tot.dua = INFINITY;
-  const double ea = c.g->pb.eps_abs, er = c.g->pb.eps_rel;
-  int budget = c.g->pb.max_admm_iter;
-  if (!c.g->pb.polish) { AdmmOut a = admm_run(c, with_collisions, keep_state, ea, er, budget); a.polish_attempts = 0; return a; }
-  double f = c.g->pb.polish_first_eps / SCP_FMAX(ea, 1e-12);
-  if (f < 1.0) f = 1.0;
-  for (int stage = 0; stage < 16 && budget > 0; ++stage) {
-    long long t0 = SCP_CLOCK();
-    AdmmOut a = admm_run(c, with_collisions, keep_state, ea * f, er * f, budget);
-    c.t_admm += SCP_CLOCK() - t0;
-#ifdef SCP_EMU_DEBUG
-    fprintf(stderr, " stage %d f=%g iters=%d solved=%d pri=%.2e dua=%.2e rho=%.3g copies=%d ncand=%d\n", stage, f, a.iters, a.solved, a.pri, a.dua, c.rho, c.copies, c.ncand);
-#endif
-    keep_state = 1;
-    tot.iters += a.iters; budget -= a.iters; tot.pri = a.pri; tot.dua = a.dua;
-    if (a.infeasible) { tot.infeasible = 1; break; }
-    if (!a.solved) break;
-    t0 = SCP_CLOCK();
-    const int pol = polish(c, with_collisions, c.g->pb.polish_rounds);
-    c.t_polish += SCP_CLOCK() - t0;
-    tot.polish_attempts++;
-    if (pol) { tot.solved = 1; tot.certified = 1; tot.pri = tot.dua = 0.0; return tot; }
-    if (f <= 1.0) { tot.solved = 1; break; }
-    f = SCP_FMAX(1.0, f * c.g->pb.polish_stage_factor);
-  }
-  return tot;
+  const long long t0 = SCP_CLOCK();
+  const long long p0 = c.t_polish;
+  AdmmOut a = admm_run(c, with_collisions, keep_state, c.g->pb.eps_abs, c.g->pb.eps_rel, c.g->pb.max_admm_iter);
+  c.t_admm += (SCP_CLOCK() - t0) - (c.t_polish - p0);
+  return a;
 }
 
 // ------------------------------------------------------------------ outputs

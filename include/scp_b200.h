@@ -57,8 +57,8 @@ typedef struct scp_b200_problem {
   double w_jerk, w_acc, w_vel, w_pos, w_col; /* row-class weights (unit rho) */
   double cand_margin;      /* collision rows kept when prev. distance < R + margin */
   double verify_tol;       /* dropped rows must hold to this tolerance */
-  double polish_first_eps; /* tolerance of the first ADMM stage before a polish attempt */
-  double polish_stage_factor; /* tolerance multiplier between stages (<1) */
+  double polish_first_eps; /* residual gate: polish is tried once pri,dua <= gate*(1+norm) and the active set has settled */
+  double polish_stage_factor; /* reserved */
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */
   int32_t reserved0;
 } scp_b200_problem;
