@@ -77,7 +77,7 @@ struct Tables {                 // constant per (K, h, weights); unit rho
 struct Layout {
   size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
   size_t c_eta, c_bound, lam, scr, red, n_double;
-  size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey;   // polish (doubles)
+  size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey, pcv, pcp;   // polish (doubles)
   size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec;          // polish (ints)
   size_t pscore, pcscore;                                               // polish (doubles)
   int pcap;
@@ -109,7 +109,7 @@ Layout make_layout(int N, int K) {
   L.xt = take(QK); L.Pt = take(QK); L.yj = take(QK); L.ya = take(QK); L.yv = take(QK); L.yp = take(QK);
   L.plam = take(L.cap);
   L.pL = take((size_t)L.pcap * L.pcap); L.pG = take((size_t)L.pcap * L.pcap); L.prhs = take(L.pcap); L.py = take(L.pcap); L.pb_ = take(L.pcap);
-  L.pex = take(L.pcap); L.pey = take(L.pcap);
+  L.pex = take(L.pcap); L.pey = take(L.pcap); L.pcv = take(L.pcap); L.pcp = take(L.pcap);
   L.pscore = take(4 * QK); L.pcscore = take(L.cap);
   L.n_double = o;
   size_t p = 0;
@@ -143,6 +143,7 @@ struct Ctx {
   scp_b200_record* rec;
   int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
   double* fused_rows;           // per-warp right-hand-side rows (shared)
+  int polish_rounds;            // add/drop rounds over all attempts of this scenario
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   // block-uniform solver state
   double rho;
@@ -837,7 +838,7 @@ SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, doubl
 // without touching a K-vector.  Then every carried row is checked (violated -> add, wrong
 // multiplier sign -> drop) until W is stable: the result satisfies the KKT conditions of the
 // carried QP to rounding, i.e. it IS its minimiser.
-struct PRow { int type, q, j, k; double ex, ey; };   // type 0 jerk,1 acc,2 vel,3 pos,4 collision(i=q,j, state k)
+struct PRow { int type, q, j, k; double ex, ey, cv, cp; };   // cv,cp = C u for the row's library vector   // type 0 jerk,1 acc,2 vel,3 pos,4 collision(i=q,j, state k)
 
 SCP_DEV double lib_dot(int t1, int k1, int t2, int k2, double h) {
   if (t1 > t2) { int t = t1; t1 = t2; t2 = t; t = k1; k1 = k2; k2 = t; }
@@ -879,12 +880,16 @@ SCP_DEV double lib_proj(const PGeom& g, int t1, int k1, int t2, int k2) {
   return lib_dot(t1, k1, t2, k2, g.h) - (c1v * (g.i00 * c2v + g.i01 * c2p) + c1p * (g.i01 * c2v + g.i11 * c2p));
 }
 
+SCP_DEV double lib_projc(const PGeom& g, const PRow& a, int ta, int ka, const PRow& b, int tb, int kb) {
+  return lib_dot(ta, ka, tb, kb, g.h) - (a.cv * (g.i00 * b.cv + g.i01 * b.cp) + a.cp * (g.i01 * b.cv + g.i11 * b.cp));
+}
+
 SCP_DEV double gram_entry(const PGeom& g, const PRow& a, const PRow& b) {
-  if (a.type < 4 && b.type < 4) return (a.q == b.q) ? lib_proj(g, a.type, a.k, b.type, b.k) : 0.0;
+  if (a.type < 4 && b.type < 4) return (a.q == b.q) ? lib_projc(g, a, a.type, a.k, b, b.type, b.k) : 0.0;
   if (a.type == 4 && b.type == 4) {
     int sgn = (a.q == b.q) + (a.j == b.j) - (a.q == b.j) - (a.j == b.q);
     if (sgn == 0) return 0.0;
-    return (double)sgn * (a.ex * b.ex + a.ey * b.ey) * lib_proj(g, 3, a.k - 1, 3, b.k - 1);
+    return (double)sgn * (a.ex * b.ex + a.ey * b.ey) * lib_projc(g, a, 3, a.k - 1, b, 3, b.k - 1);
   }
   const PRow& d = a.type < 4 ? a : b;
   const PRow& cr = a.type < 4 ? b : a;
@@ -892,13 +897,14 @@ SCP_DEV double gram_entry(const PGeom& g, const PRow& a, const PRow& b) {
   double coef = (ag == cr.q) ? 1.0 : ((ag == cr.j) ? -1.0 : 0.0);
   if (coef == 0.0) return 0.0;
   coef *= (d.q & 1) ? cr.ey : cr.ex;
-  return coef * lib_proj(g, d.type, d.k, 3, cr.k - 1);
+  return coef * lib_projc(g, d, d.type, d.k, cr, 3, cr.k - 1);
 }
 
 SCP_DEV PRow load_prow(Ctx& c, int r) {
   PRow w;
   w.type = (c.wi + c.g->L.ptype)[r]; w.q = (c.wi + c.g->L.pq)[r]; w.j = (c.wi + c.g->L.pj2)[r];
   w.k = (c.wi + c.g->L.pk)[r]; w.ex = (c.wd + c.g->L.pex)[r]; w.ey = (c.wd + c.g->L.pey)[r];
+  w.cv = (c.wd + c.g->L.pcv)[r]; w.cp = (c.wd + c.g->L.pcp)[r];
   return w;
 }
 
@@ -913,6 +919,8 @@ SCP_DEV int polish_compact(Ctx& c, int use_col) {
   int *ptype = c.wi + c.g->L.ptype, *pq = c.wi + c.g->L.pq, *pj2 = c.wi + c.g->L.pj2, *pk = c.wi + c.g->L.pk,
       *psgn = c.wi + c.g->L.psgn;
   double *pb = c.wd + c.g->L.pb_, *pex = c.wd + c.g->L.pex, *pey = c.wd + c.g->L.pey;
+  double *pcv = c.wd + c.g->L.pcv, *pcp = c.wd + c.g->L.pcp;
+  const double hstep = c.g->pb.time_step;
   const double* ceta = c.wd + c.g->L.c_eta;
   const double* cb = c.wd + c.g->L.c_bound;
   const double* off = c.wd + c.g->L.off;
@@ -951,6 +959,7 @@ SCP_DEV int polish_compact(Ctx& c, int use_col) {
         else if (cls == 2) b = (m > 0 ? vl : -vl) - c.v0[q];
         else b = (m > 0 ? hi[q & 1] : lo[q & 1]) - off[e];
         pb[base] = b;
+        pcv[base] = lib_dot(cls, k, 2, K - 1, hstep); pcp[base] = lib_dot(cls, k, 3, K - 1, hstep);
         ++base;
       } else {
         int t = u - 4 * QK, k = 1 + t / N, i = t - (k - 1) * N;
@@ -960,6 +969,7 @@ SCP_DEV int polish_compact(Ctx& c, int use_col) {
             ptype[base] = 4; pq[base] = i; pj2[base] = j; pk[base] = k; psgn[base] = -1;
             double ex = ceta[2 * sidx], ey = ceta[2 * sidx + 1];
             pex[base] = ex; pey[base] = ey;
+            pcv[base] = lib_dot(3, k - 1, 2, K - 1, hstep); pcp[base] = lib_dot(3, k - 1, 3, K - 1, hstep);
             // eta.(p_i - p_j) >= bound with p = off[k-1] + S_{k-1} x
             pb[base] = cb[sidx] - (ex * (off[(2 * i) * K + k - 1] - off[(2 * j) * K + k - 1]) +
                                    ey * (off[(2 * i + 1) * K + k - 1] - off[(2 * j + 1) * K + k - 1]));
@@ -987,24 +997,25 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
   // assemble G (lower) and rhs = 2 (A_W x_d - b)
   SCP_PHASE(c) {
     double dmax = 0.0;
-    for (int e = tid; e < n * n; e += c.nthreads) {
-      int col = e / n, row = e - col * n;
-      if (row < col) continue;
-      PRow a = load_prow(c, row), b = load_prow(c, col);
-      double v = gram_entry(g, a, b);
-      A[(size_t)col * ld + row] = v;
-      G0[(size_t)col * ld + row] = v;
-      if (row == col) dmax = SCP_FMAX(dmax, v);
+    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
+      const PRow b = load_prow(c, col);
+      for (int row = col + (tid & 31); row < n; row += 32) {
+        PRow a = load_prow(c, row);
+        double v = gram_entry(g, a, b);
+        A[(size_t)col * ld + row] = v;
+        G0[(size_t)col * ld + row] = v;
+        if (row == col) dmax = SCP_FMAX(dmax, v);
+      }
     }
     for (int r = tid; r < n; r += c.nthreads) {
       PRow a = load_prow(c, r);
       double axd = 0.0;
       if (a.type < 4) {
-        double cv = lib_dot(a.type, a.k, 2, g.K - 1, g.h), cp = lib_dot(a.type, a.k, 3, g.K - 1, g.h);
+        double cv = a.cv, cp = a.cp;
         double d0 = deq[2 * a.q], d1 = deq[2 * a.q + 1];
         axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
       } else {
-        double cv = lib_dot(3, a.k - 1, 2, g.K - 1, g.h), cp = lib_dot(3, a.k - 1, 3, g.K - 1, g.h);
+        double cv = a.cv, cp = a.cp;
         double d0 = a.ex * (deq[2 * (2 * a.q)] - deq[2 * (2 * a.j)]) + a.ey * (deq[2 * (2 * a.q + 1)] - deq[2 * (2 * a.j + 1)]);
         double d1 = a.ex * (deq[2 * (2 * a.q) + 1] - deq[2 * (2 * a.j) + 1]) + a.ey * (deq[2 * (2 * a.q + 1) + 1] - deq[2 * (2 * a.j + 1) + 1]);
         axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
@@ -1021,11 +1032,11 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
   double* colb = c.sm;                      // n <= pcap <= RED
   double* rowb = c.sm + RED;
   SCP_PHASE(c) {
-    for (int e = tid; e < n * n; e += c.nthreads) {
-      int col = e / n, row = e - col * n;
-      if (row < col) A[(size_t)col * ld + row] = G0[(size_t)row * ld + col];
-      else if (row == col) A[(size_t)col * ld + row] += delta;
-    }
+    for (int col = tid >> 5; col < n; col += c.nthreads >> 5)
+      for (int row = tid & 31; row <= col; row += 32) {
+        if (row < col) A[(size_t)col * ld + row] = G0[(size_t)row * ld + col];
+        else A[(size_t)col * ld + row] += delta;
+      }
   }
   SCP_SYNC(c);
   int ok = 1;
@@ -1038,13 +1049,11 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
     if (!(piv > 0.0)) ok = 0;
     const double ip = ok ? 1.0 / piv : 0.0;
     SCP_PHASE(c) {
-      for (int e = tid; e < n * n; e += c.nthreads) {
-        int col = e / n, row = e - col * n;
-        double v;
-        if (row == p) v = (col == p) ? ip : rowb[col] * ip;
-        else if (col == p) v = -colb[row] * ip;
-        else v = A[(size_t)col * ld + row] - colb[row] * rowb[col] * ip;
-        A[(size_t)col * ld + row] = v;
+      for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
+        const double rc = rowb[col] * ip;
+        double* Ac = A + (size_t)col * ld;
+        if (col == p) { for (int row = tid & 31; row < n; row += 32) Ac[row] = (row == p) ? ip : -colb[row] * ip; }
+        else { for (int row = tid & 31; row < n; row += 32) Ac[row] = (row == p) ? rc : Ac[row] - colb[row] * rc; }
       }
     }
     SCP_SYNC(c);
@@ -1122,6 +1131,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
         v = vp[e]; mp = v > hi[a2] - off[e] ? 1 : (v < lo[a2] - off[e] ? -1 : 0);
       }
       pmark[e] = mj; pmark[2 * QK + e] = mv; pmark[3 * QK + e] = mp;
+      for (int cls = 0; cls < 4; ++cls) { pdec[cls * QK + e] = pmark[cls * QK + e]; pscore[cls * QK + e] = 0.0; }
     }
     if (use_col)
       for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
@@ -1133,6 +1143,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   SCP_SYNC(c);
 
   for (int round = 0; round < max_rounds; ++round) {
+    c.polish_rounds++;
     const int n = polish_compact(c, use_col);
     if (n < 0) return 0;
     if (n > 0 && !polish_solve(c, n, g)) return 0;
@@ -1280,7 +1291,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
       mdrop = SCP_FMAX(mdrop, reduce_finish(c, 0, 0));
     }
 #ifdef SCP_EMU_DEBUG
-    fprintf(stderr, "  polish round %d n=%d changes=%g broken=%g\n", round, n, changes, broken);
+    if (broken > 0.0) fprintf(stderr, "  POLISH BROKEN at round %d n=%d\n", round, n);
 #endif
     if (broken > 0.0) return 0;             // active rows not met as equalities: inconsistent (infeasible) set
     if (changes > 0.0) {
@@ -1301,6 +1312,10 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
       }
       SCP_SYNC(c);
     }
+#ifdef SCP_EMU_DEBUG
+    if (changes == 0.0) fprintf(stderr, "  POLISH OK after %d rounds n=%d\n", round + 1, n);
+    else if (round == max_rounds - 1) fprintf(stderr, "  POLISH FAIL after %d rounds n=%d changes=%g\n", round + 1, n, changes);
+#endif
     if (changes == 0.0) {
       // accept: x, P, and an ADMM state consistent with (x, y): v = bound + y/(rho r) on active rows,
       // v = row value elsewhere; lam = plam; F = FY (2 lam' - lam with lam' = lam)
@@ -1631,14 +1646,14 @@ SCP_DEV void solve_scenario(Ctx& c) {
   scp_b200_record r;
   r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
   r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
-  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
+  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.polish_rounds = 0; r.reserved2 = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
   r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
   r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
   r.cand_row_iters = 0;
   for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
 
   setup_scenario(c);
-  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0;
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0;
   const long long t_begin = SCP_CLOCK();
   factor_operator(c);
   AdmmOut a0 = solve_qp(c, 0, 0);
@@ -1716,7 +1731,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
   SCP_SYNC(c);
   r.objective = reduce_finish(c, 0, 1);
   write_outputs(c);
-  r.cycles_total = SCP_CLOCK() - t_begin; r.cycles_admm = c.t_admm; r.cycles_polish = c.t_polish;
+  r.cycles_total = SCP_CLOCK() - t_begin; r.cycles_admm = c.t_admm; r.cycles_polish = c.t_polish; r.polish_rounds = c.polish_rounds;
   SCP_PHASE(c) { if (tid == 0) *c.rec = r; }
   SCP_SYNC(c);
 }

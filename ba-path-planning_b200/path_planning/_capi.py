@@ -75,6 +75,8 @@ class Record(C.Structure):
         ("cycles_total", C.c_int64),
         ("cycles_admm", C.c_int64),
         ("cycles_polish", C.c_int64),
+        ("polish_rounds", C.c_int32),
+        ("reserved2", C.c_int32),
         ("rel_step", C.c_double * MAX_SCP_ITER),
     ]
 
@@ -174,7 +176,7 @@ def record_to_dict(r: Record) -> dict:
         initial_feasible=bool(r.initial_feasible), admm_iterations=int(r.admm_iterations),
         qp_unsolved=int(r.qp_unsolved), rebuilds=int(r.rebuilds), max_copies=int(r.max_copies),
         first_violation=tuple(int(v) for v in r.first_violation), polish_ok=int(r.polish_ok), qp_infeasible=int(r.qp_infeasible), polish_attempts=int(r.polish_attempts),
-        cycles_total=int(r.cycles_total), cycles_admm=int(r.cycles_admm), cycles_polish=int(r.cycles_polish),
+        cycles_total=int(r.cycles_total), cycles_admm=int(r.cycles_admm), cycles_polish=int(r.cycles_polish), polish_rounds=int(r.polish_rounds),
         first_violation_dist=float(r.first_violation_dist), min_separation=float(r.min_separation),
         objective=float(r.objective), pri_res=float(r.pri_res), dua_res=float(r.dua_res), cand_row_iters=float(r.cand_row_iters),
         rel_steps=[float(r.rel_step[i]) for i in range(n)],

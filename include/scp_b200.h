@@ -83,6 +83,8 @@ typedef struct scp_b200_record {
   double pri_res, dua_res; /* of the last subproblem */
   double cand_row_iters;   /* sum over ADMM iterations of collision rows actually carried */
   int64_t cycles_total, cycles_admm, cycles_polish; /* SM clock cycles spent on this scenario */
+  int32_t polish_rounds;   /* add/drop rounds over all polish attempts */
+  int32_t reserved2;
   double rel_step[SCP_B200_MAX_SCP_ITER]; /* scp.py:157-160, one per trip */
 } scp_b200_record;
 
