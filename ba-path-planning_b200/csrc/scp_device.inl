@@ -78,7 +78,7 @@ struct Layout {
   size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
   size_t c_eta, c_bound, lam, scr, red, n_double;
   size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey, pcv, pcp;   // polish (doubles)
-  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec;          // polish (ints)
+  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec, ppos, pcpos, pcown, pid, chg;   // polish (ints)
   size_t pscore, pcscore;                                               // polish (doubles)
   int pcap;
   size_t cnt, coff, c_j, flags, n_int;
@@ -103,7 +103,7 @@ Layout make_layout(int N, int K) {
   L.off = take(QK); L.deq = take(2 * Q); L.mu = take(2 * Q);
   L.cap = (size_t)N * (size_t)K * (size_t)(N > 1 ? N - 1 : 1);
   L.c_eta = take(2 * L.cap); L.c_bound = take(L.cap); L.lam = take((size_t)N * N * K);
-  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 2 * Q + 2100);
+  L.scr = take(3 * Q * ((size_t)(K + CH - 1) / CH) + 2 * Q + 2100 + 2 * 1024);
   L.red = take(4 * RED);
   L.pcap = 12 * N + 128; if (L.pcap > 1024) L.pcap = 1024;
   L.xt = take(QK); L.Pt = take(QK); L.yj = take(QK); L.ya = take(QK); L.yv = take(QK); L.yp = take(QK);
@@ -116,6 +116,7 @@ Layout make_layout(int N, int K) {
   auto takei = [&](size_t n) { size_t r = p; p += (n + 3) & ~(size_t)3; return r; };
   L.cnt = takei((size_t)N * K + 1); L.coff = takei((size_t)N * K + 1); L.c_j = takei(L.cap); L.flags = takei(((size_t)N * N * K + 3) / 4);
   L.pmark = takei(4 * QK); L.pcmark = takei(L.cap); L.pdec = takei(4 * QK); L.pcdec = takei(L.cap);
+  L.ppos = takei(4 * QK); L.pcpos = takei(L.cap); L.pcown = takei(L.cap); L.pid = takei(L.pcap); L.chg = takei(L.pcap);
   L.ptype = takei(L.pcap); L.pq = takei(L.pcap); L.pj2 = takei(L.pcap); L.pk = takei(L.pcap); L.psgn = takei(L.pcap);
   L.n_int = p;
   return L;
@@ -909,165 +910,239 @@ SCP_DEV PRow load_prow(Ctx& c, int r) {
 }
 
 // marks: dyn rows pmark[cls*QK + e] in {-1 lower, 0, +1 upper}; collision entries pcmark[s] in {0,1}
-// (only the i<j owner's entry is used).  Returns the number of active rows, or -1 if > cap.
-SCP_DEV int polish_compact(Ctx& c, int use_col) {
-  const int K = c.K, N = c.N, QK = c.Q * K;
-  const int* pmark = c.wi + c.g->L.pmark;
-  const int* pcmark = c.wi + c.g->L.pcmark;
-  const int* coff = c.wi + c.g->L.coff;
-  const int* cj = c.wi + c.g->L.c_j;
-  int *ptype = c.wi + c.g->L.ptype, *pq = c.wi + c.g->L.pq, *pj2 = c.wi + c.g->L.pj2, *pk = c.wi + c.g->L.pk,
-      *psgn = c.wi + c.g->L.psgn;
-  double *pb = c.wd + c.g->L.pb_, *pex = c.wd + c.g->L.pex, *pey = c.wd + c.g->L.pey;
-  double *pcv = c.wd + c.g->L.pcv, *pcp = c.wd + c.g->L.pcp;
-  const double hstep = c.g->pb.time_step;
-  const double* ceta = c.wd + c.g->L.c_eta;
-  const double* cb = c.wd + c.g->L.c_bound;
+// (both owners' entries carry the mark; the i<j entry is the row's identity).
+//
+// The active rows live in a list (ptype/pq/pj2/pk/psgn/pb/pex/pey/pcv/pcp, n entries) together with
+//   G0   = A_W Pi A_W'            (n x n, full symmetric storage, column stride ld)
+//   Ainv = (G0 + delta I)^-1      (same storage)
+// and the list position of every marked row (ppos / pcpos).  Rows enter and leave one at a time with
+// O(n^2) bordered-inverse updates (add: Schur complement of the new row; drop: rank-one downdate, then
+// the last row moves into the hole), so a round that changes c rows costs c n^2 instead of n^3.
+
+// list slot `slot` <- box row (cls, e) active at its upper (m>0) / lower (m<0) bound
+SCP_DEV void polish_fill_dyn(Ctx& c, int slot, int cls, int e, int m) {
+  const int K = c.K, q = e / K, k = e - q * K;
+  const double h = c.g->pb.time_step;
+  (c.wi + c.g->L.ptype)[slot] = cls; (c.wi + c.g->L.pq)[slot] = q; (c.wi + c.g->L.pj2)[slot] = -1;
+  (c.wi + c.g->L.pk)[slot] = k; (c.wi + c.g->L.psgn)[slot] = m;
+  (c.wd + c.g->L.pex)[slot] = 0.0; (c.wd + c.g->L.pey)[slot] = 0.0;
+  double b;
+  if (cls == 0) b = m > 0 ? c.g->pb.jerk_limit : -c.g->pb.jerk_limit;
+  else if (cls == 1) b = m > 0 ? c.g->pb.acc_limit : -c.g->pb.acc_limit;
+  else if (cls == 2) b = (m > 0 ? c.g->pb.vel_limit : -c.g->pb.vel_limit) - c.v0[q];
+  else b = (m > 0 ? c.g->pb.space[2 + (q & 1)] : c.g->pb.space[q & 1]) - (c.wd + c.g->L.off)[e];
+  (c.wd + c.g->L.pb_)[slot] = b;
+  (c.wd + c.g->L.pcv)[slot] = lib_dot(cls, k, 2, K - 1, h);
+  (c.wd + c.g->L.pcp)[slot] = lib_dot(cls, k, 3, K - 1, h);
+}
+
+// list slot `slot` <- collision row of CSR entry sidx (owner i < partner j, state k)
+SCP_DEV void polish_fill_col(Ctx& c, int slot, int sidx, int k, int i) {
+  const int K = c.K;
+  const double h = c.g->pb.time_step;
+  const int j = (c.wi + c.g->L.c_j)[sidx];
+  const double ex = (c.wd + c.g->L.c_eta)[2 * sidx], ey = (c.wd + c.g->L.c_eta)[2 * sidx + 1];
   const double* off = c.wd + c.g->L.off;
-  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
-  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
-  const int total = 4 * QK + (use_col ? (K - 1) * N : 0);   // dyn marks, then one unit per (k,i) owner segment
+  (c.wi + c.g->L.ptype)[slot] = 4; (c.wi + c.g->L.pq)[slot] = i; (c.wi + c.g->L.pj2)[slot] = j;
+  (c.wi + c.g->L.pk)[slot] = k; (c.wi + c.g->L.psgn)[slot] = -1;
+  (c.wd + c.g->L.pex)[slot] = ex; (c.wd + c.g->L.pey)[slot] = ey;
+  // eta.(p_i - p_j) >= bound with p = off[k-1] + S_{k-1} x
+  (c.wd + c.g->L.pb_)[slot] = (c.wd + c.g->L.c_bound)[sidx] -
+      (ex * (off[(2 * i) * K + k - 1] - off[(2 * j) * K + k - 1]) + ey * (off[(2 * i + 1) * K + k - 1] - off[(2 * j + 1) * K + k - 1]));
+  (c.wd + c.g->L.pcv)[slot] = lib_dot(3, k - 1, 2, K - 1, h);
+  (c.wd + c.g->L.pcp)[slot] = lib_dot(3, k - 1, 3, K - 1, h);
+}
+
+// rhs entry 2 (a_r . x_d - b_r) of list row r
+SCP_DEV double polish_rhs_entry(Ctx& c, const PGeom& g, int r) {
+  const PRow a = load_prow(c, r);
+  const double* deq = c.wd + c.g->L.deq;
+  double d0, d1;
+  if (a.type < 4) { d0 = deq[2 * a.q]; d1 = deq[2 * a.q + 1]; }
+  else {
+    d0 = a.ex * (deq[2 * (2 * a.q)] - deq[2 * (2 * a.j)]) + a.ey * (deq[2 * (2 * a.q + 1)] - deq[2 * (2 * a.j + 1)]);
+    d1 = a.ex * (deq[2 * (2 * a.q) + 1] - deq[2 * (2 * a.j) + 1]) + a.ey * (deq[2 * (2 * a.q + 1) + 1] - deq[2 * (2 * a.j + 1) + 1]);
+  }
+  const double axd = a.cv * (g.i00 * d0 + g.i01 * d1) + a.cp * (g.i01 * d0 + g.i11 * d1);
+  return 2.0 * (axd - (c.wd + c.g->L.pb_)[r]);
+}
+
+// Row in list slot n joins the set: returns 0 on a non-positive Schur complement.
+SCP_DEV int polish_add(Ctx& c, const PGeom& g, int n) {
+  const int ld = c.g->L.pcap;
+  double* A = c.wd + c.g->L.pL;
+  double* G0 = c.wd + c.g->L.pG;
+  double* gv = c.wd + c.g->L.scr;                // n+1
+  double* u = gv + c.g->L.pcap;                  // n
+  double* red = c.sm;
+  SCP_PHASE(c) {
+    const PRow nw = load_prow(c, n);
+    for (int i = tid; i <= n; i += c.nthreads) {
+      const PRow a = load_prow(c, i);
+      const double v = gram_entry(g, a, nw);
+      gv[i] = v; G0[(size_t)n * ld + i] = v; G0[(size_t)i * ld + n] = v;
+    }
+    if (tid == 0) (c.wd + c.g->L.prhs)[n] = polish_rhs_entry(c, g, n);
+  }
+  SCP_SYNC(c);
+  SCP_PHASE(c) {
+    double part = 0.0;
+    for (int i = tid; i < n; i += c.nthreads) {
+      double acc = 0.0;
+      for (int j = 0; j < n; ++j) acc += A[(size_t)j * ld + i] * gv[j];
+      u[i] = acc; part += acc * gv[i];
+    }
+    red[tid] = part;
+  }
+  SCP_SYNC(c);
+  const double gtu = reduce_finish(c, 0, 1);
+  const double gnn = gv[n];
+  const double sch = gnn * (1.0 + 1e-11) - gtu;
+  if (!(sch > 0.0)) return 0;
+  const double is = 1.0 / sch;
+  SCP_PHASE(c) {
+    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
+      const double uc = u[col] * is;
+      double* Ac = A + (size_t)col * ld;
+      for (int row = tid & 31; row < n; row += 32) Ac[row] += u[row] * uc;
+    }
+    for (int i = tid; i < n; i += c.nthreads) { A[(size_t)n * ld + i] = -u[i] * is; A[(size_t)i * ld + n] = -u[i] * is; }
+    if (tid == 0) A[(size_t)n * ld + n] = is;
+  }
+  SCP_SYNC(c);
+  return 1;
+}
+
+// Row at list position p leaves the set; the last row moves into the hole.  Returns the new n.
+SCP_DEV int polish_drop(Ctx& c, int p, int n) {
+  const int ld = c.g->L.pcap, K = c.K, QK = c.Q * K;
+  double* A = c.wd + c.g->L.pL;
+  double* G0 = c.wd + c.g->L.pG;
+  double* cpv = c.wd + c.g->L.scr;
+  SCP_PHASE(c) { for (int i = tid; i < n; i += c.nthreads) cpv[i] = A[(size_t)p * ld + i]; }
+  SCP_SYNC(c);
+  const double iapp = 1.0 / cpv[p];
+  SCP_PHASE(c) {
+    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
+      const double cc = cpv[col] * iapp;
+      double* Ac = A + (size_t)col * ld;
+      for (int row = tid & 31; row < n; row += 32) Ac[row] -= cpv[row] * cc;
+    }
+  }
+  SCP_SYNC(c);
+  const int last = n - 1;
+  if (p != last) {
+    SCP_PHASE(c) {
+      for (int i = tid; i < n; i += c.nthreads) { A[(size_t)p * ld + i] = A[(size_t)last * ld + i]; G0[(size_t)p * ld + i] = G0[(size_t)last * ld + i]; }
+    }
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      for (int i = tid; i < last; i += c.nthreads) { A[(size_t)i * ld + p] = A[(size_t)i * ld + last]; G0[(size_t)i * ld + p] = G0[(size_t)i * ld + last]; }
+      if (tid == 0) {
+        int* ptype = c.wi + c.g->L.ptype; int* pq = c.wi + c.g->L.pq; int* pj2 = c.wi + c.g->L.pj2;
+        int* pk = c.wi + c.g->L.pk; int* psgn = c.wi + c.g->L.psgn; int* pid = c.wi + c.g->L.pid;
+        ptype[p] = ptype[last]; pq[p] = pq[last]; pj2[p] = pj2[last]; pk[p] = pk[last]; psgn[p] = psgn[last]; pid[p] = pid[last];
+        double* base = c.wd;
+        const size_t offs[7] = {c.g->L.pb_, c.g->L.pex, c.g->L.pey, c.g->L.pcv, c.g->L.pcp, c.g->L.prhs, c.g->L.py};
+        for (int f = 0; f < 7; ++f) (base + offs[f])[p] = (base + offs[f])[last];
+        const int id = pid[p];
+        if (id < 4 * QK) (c.wi + c.g->L.ppos)[id] = p; else (c.wi + c.g->L.pcpos)[id - 4 * QK] = p;
+      }
+    }
+    SCP_SYNC(c);
+  }
+  return last;
+}
+
+// Applies the pending mark changes (pdec vs pmark / pcdec vs pcmark, score >= threshold) one row at a time.
+// Returns the new n, or -1 when the set outgrows the list or an update breaks down.
+SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_add, double thr_drop) {
+  const int K = c.K, N = c.N, QK = c.Q * K;
+  int* pmark = c.wi + c.g->L.pmark; int* pcmark = c.wi + c.g->L.pcmark;
+  const int* pdec = c.wi + c.g->L.pdec; const int* pcdec = c.wi + c.g->L.pcdec;
+  const double* pscore = c.wd + c.g->L.pscore; const double* pcscore = c.wd + c.g->L.pcscore;
+  int* ppos = c.wi + c.g->L.ppos; int* pcpos = c.wi + c.g->L.pcpos; int* pid = c.wi + c.g->L.pid;
+  int* chg = c.wi + c.g->L.chg;
+  const int* pcown = c.wi + c.g->L.pcown;
+  const int* coff = c.wi + c.g->L.coff; const int* cj = c.wi + c.g->L.c_j;
+  const int total = 4 * QK + (use_col ? c.ncand : 0);
   const int per = (total + c.nthreads - 1) / c.nthreads;
   int* part = (int*)(c.sm + 2 * RED);
   SCP_PHASE(c) {
-    int n = 0;
+    int cnt = 0;
     for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
-      if (u < 4 * QK) n += (pmark[u] != 0);
-      else {
-        int t = u - 4 * QK, k = 1 + t / N, i = t - (k - 1) * N;
-        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) n += (cj[sidx] > i && pcmark[sidx]);
-      }
+      if (u < 4 * QK) { const int nm = pdec[u]; cnt += (nm != pmark[u] && pscore[u] >= (nm != 0 ? thr_add : thr_drop)); }
+      else { const int sidx = u - 4 * QK, nm = pcdec[sidx]; cnt += (pcown[sidx] >= 0 && nm != pcmark[sidx] && pcscore[sidx] >= (nm != 0 ? thr_add : thr_drop)); }
     }
-    part[tid] = n;
+    part[tid] = cnt;
   }
   SCP_SYNC(c);
-  int ntot = 0;
-  for (int e = 0; e < c.nthreads; ++e) ntot += part[e];
-  if (ntot > c.g->L.pcap) { SCP_SYNC(c); return -1; }
+  int nchg = 0;
+  for (int e = 0; e < c.nthreads; ++e) nchg += part[e];
+  const int chg_cap = c.g->L.pcap;
   SCP_PHASE(c) {
     int base = 0;
     for (int e = 0; e < tid; ++e) base += part[e];
     for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
-      if (u < 4 * QK) {
-        int m = pmark[u];
-        if (!m) continue;
-        int cls = u / QK, e = u - cls * QK, q = e / K, k = e - q * K;
-        ptype[base] = cls; pq[base] = q; pj2[base] = -1; pk[base] = k; psgn[base] = m; pex[base] = 0; pey[base] = 0;
-        double b;
-        if (cls == 0) b = m > 0 ? jl : -jl;
-        else if (cls == 1) b = m > 0 ? al : -al;
-        else if (cls == 2) b = (m > 0 ? vl : -vl) - c.v0[q];
-        else b = (m > 0 ? hi[q & 1] : lo[q & 1]) - off[e];
-        pb[base] = b;
-        pcv[base] = lib_dot(cls, k, 2, K - 1, hstep); pcp[base] = lib_dot(cls, k, 3, K - 1, hstep);
-        ++base;
-      } else {
-        int t = u - 4 * QK, k = 1 + t / N, i = t - (k - 1) * N;
-        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
-          int j = cj[sidx];
-          if (j > i && pcmark[sidx]) {
-            ptype[base] = 4; pq[base] = i; pj2[base] = j; pk[base] = k; psgn[base] = -1;
-            double ex = ceta[2 * sidx], ey = ceta[2 * sidx + 1];
-            pex[base] = ex; pey[base] = ey;
-            pcv[base] = lib_dot(3, k - 1, 2, K - 1, hstep); pcp[base] = lib_dot(3, k - 1, 3, K - 1, hstep);
-            // eta.(p_i - p_j) >= bound with p = off[k-1] + S_{k-1} x
-            pb[base] = cb[sidx] - (ex * (off[(2 * i) * K + k - 1] - off[(2 * j) * K + k - 1]) +
-                                   ey * (off[(2 * i + 1) * K + k - 1] - off[(2 * j + 1) * K + k - 1]));
-            ++base;
-          }
+      int hit;
+      if (u < 4 * QK) { const int nm = pdec[u]; hit = (nm != pmark[u] && pscore[u] >= (nm != 0 ? thr_add : thr_drop)); }
+      else { const int sidx = u - 4 * QK, nm = pcdec[sidx]; hit = (pcown[sidx] >= 0 && nm != pcmark[sidx] && pcscore[sidx] >= (nm != 0 ? thr_add : thr_drop)); }
+      if (hit) { if (base < chg_cap) chg[base] = u; ++base; }
+    }
+  }
+  SCP_SYNC(c);
+  if (nchg > chg_cap) nchg = chg_cap;
+  for (int ci = 0; ci < nchg; ++ci) {
+    const int id = chg[ci];
+    if (id < 4 * QK) {
+      const int m = pmark[id], nm = pdec[id];
+      if (m != 0) { n = polish_drop(c, ppos[id], n); SCP_PHASE(c) { if (tid == 0) ppos[id] = -1; } SCP_SYNC(c); }
+      if (nm != 0) {
+        if (n >= c.g->L.pcap) return -1;
+        SCP_PHASE(c) { if (tid == 0) { polish_fill_dyn(c, n, id / QK, id % QK, nm); pid[n] = id; ppos[id] = n; } }
+        SCP_SYNC(c);
+        if (!polish_add(c, g, n)) return -1;
+        ++n;
+      }
+      SCP_PHASE(c) { if (tid == 0) pmark[id] = nm; }
+      SCP_SYNC(c);
+    } else {
+      const int sidx = id - 4 * QK;
+      const int m = pcmark[sidx], nm = pcdec[sidx];
+      const int t = pcown[sidx], k = t / N, i = t - k * N, j = cj[sidx];
+      if (m != 0) { n = polish_drop(c, pcpos[sidx], n); SCP_PHASE(c) { if (tid == 0) pcpos[sidx] = -1; } SCP_SYNC(c); }
+      else {
+        if (n >= c.g->L.pcap) return -1;
+        SCP_PHASE(c) { if (tid == 0) { polish_fill_col(c, n, sidx, k, i); pid[n] = id; pcpos[sidx] = n; } }
+        SCP_SYNC(c);
+        if (!polish_add(c, g, n)) return -1;
+        ++n;
+      }
+      SCP_PHASE(c) {
+        if (tid == 0) {
+          pcmark[sidx] = nm;
+          for (int s2 = coff[k * N + j]; s2 < coff[k * N + j + 1]; ++s2) if (cj[s2] == i) pcmark[s2] = nm;   // mirror entry
         }
       }
+      SCP_SYNC(c);
     }
   }
-  SCP_SYNC(c);
-  return ntot;
+  return n;
 }
 
-// Solve (G + delta I) y = rhs through an explicit inverse, with two refinement sweeps on G.  Returns 0 on breakdown.
-SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
+// y = Ainv rhs with two refinement sweeps on G0
+SCP_DEV void polish_solve(Ctx& c, int n) {
   const int ld = c.g->L.pcap;
-  double* A = c.wd + c.g->L.pL;           // column-major lower triangle: A[col*ld + row]
-  double* G0 = c.wd + c.g->L.pG;          // untouched copy of G for the refinement residual
-  double* rhs = c.wd + c.g->L.prhs;
+  const double* A = c.wd + c.g->L.pL;
+  const double* G0 = c.wd + c.g->L.pG;
+  const double* rhs = c.wd + c.g->L.prhs;
   double* y = c.wd + c.g->L.py;
-  double* rhs2 = c.wd + c.g->L.scr + c.g->L.pcap;
-  const double* pb = c.wd + c.g->L.pb_;
-  const double* deq = c.wd + c.g->L.deq;
-  double* red = c.sm;
-  // assemble G (lower) and rhs = 2 (A_W x_d - b)
-  SCP_PHASE(c) {
-    double dmax = 0.0;
-    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
-      const PRow b = load_prow(c, col);
-      for (int row = col + (tid & 31); row < n; row += 32) {
-        PRow a = load_prow(c, row);
-        double v = gram_entry(g, a, b);
-        A[(size_t)col * ld + row] = v;
-        G0[(size_t)col * ld + row] = v;
-        if (row == col) dmax = SCP_FMAX(dmax, v);
-      }
-    }
-    for (int r = tid; r < n; r += c.nthreads) {
-      PRow a = load_prow(c, r);
-      double axd = 0.0;
-      if (a.type < 4) {
-        double cv = a.cv, cp = a.cp;
-        double d0 = deq[2 * a.q], d1 = deq[2 * a.q + 1];
-        axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
-      } else {
-        double cv = a.cv, cp = a.cp;
-        double d0 = a.ex * (deq[2 * (2 * a.q)] - deq[2 * (2 * a.j)]) + a.ey * (deq[2 * (2 * a.q + 1)] - deq[2 * (2 * a.j + 1)]);
-        double d1 = a.ex * (deq[2 * (2 * a.q) + 1] - deq[2 * (2 * a.j) + 1]) + a.ey * (deq[2 * (2 * a.q + 1) + 1] - deq[2 * (2 * a.j + 1) + 1]);
-        axd = cv * (g.i00 * d0 + g.i01 * d1) + cp * (g.i01 * d0 + g.i11 * d1);
-      }
-      rhs[r] = 2.0 * (axd - pb[r]);
-      y[r] = 0.0;
-    }
-    red[tid] = dmax;
-  }
-  SCP_SYNC(c);
-  const double delta = 1e-11 * SCP_FMAX(reduce_finish(c, 0, 0), 1e-300);
-  // A <- (G + delta I)^-1 by in-place Gauss-Jordan on the full symmetric matrix: every pivot is one fully
-  // parallel n x n update between two barriers (no sequential substitutions).  SPD => no pivoting.
-  double* colb = c.sm;                      // n <= pcap <= RED
-  double* rowb = c.sm + RED;
-  SCP_PHASE(c) {
-    for (int col = tid >> 5; col < n; col += c.nthreads >> 5)
-      for (int row = tid & 31; row <= col; row += 32) {
-        if (row < col) A[(size_t)col * ld + row] = G0[(size_t)row * ld + col];
-        else A[(size_t)col * ld + row] += delta;
-      }
-  }
-  SCP_SYNC(c);
-  int ok = 1;
-  for (int p = 0; p < n; ++p) {
-    SCP_PHASE(c) {
-      for (int e = tid; e < n; e += c.nthreads) { colb[e] = A[(size_t)p * ld + e]; rowb[e] = A[(size_t)e * ld + p]; }
-    }
-    SCP_SYNC(c);
-    const double piv = colb[p];
-    if (!(piv > 0.0)) ok = 0;
-    const double ip = ok ? 1.0 / piv : 0.0;
-    SCP_PHASE(c) {
-      for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
-        const double rc = rowb[col] * ip;
-        double* Ac = A + (size_t)col * ld;
-        if (col == p) { for (int row = tid & 31; row < n; row += 32) Ac[row] = (row == p) ? ip : -colb[row] * ip; }
-        else { for (int row = tid & 31; row < n; row += 32) Ac[row] = (row == p) ? rc : Ac[row] - colb[row] * rc; }
-      }
-    }
-    SCP_SYNC(c);
-    if (!ok) return 0;
-  }
-  // y = Ainv rhs, then two refinement sweeps on the unregularised G
-  double* z = c.wd + c.g->L.scr;           // n <= pcap <= scr size (see make_layout)
+  double* z = c.wd + c.g->L.scr;
   for (int sweep = 0; sweep < 3; ++sweep) {
     SCP_PHASE(c) {
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = rhs[r];
-        if (sweep > 0)
-          for (int q2 = 0; q2 < n; ++q2)
-            acc -= (q2 <= r ? G0[(size_t)q2 * ld + r] : G0[(size_t)r * ld + q2]) * y[q2];
+        if (sweep > 0) for (int q2 = 0; q2 < n; ++q2) acc -= G0[(size_t)q2 * ld + r] * y[q2];
         z[r] = acc;
       }
     }
@@ -1076,14 +1151,11 @@ SCP_DEV int polish_solve(Ctx& c, int n, const PGeom& g) {
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = 0.0;
         for (int q2 = 0; q2 < n; ++q2) acc += A[(size_t)q2 * ld + r] * z[q2];
-        rhs2[r] = acc;
+        y[r] = (sweep > 0 ? y[r] : 0.0) + acc;
       }
     }
     SCP_SYNC(c);
-    SCP_PHASE(c) { for (int r = tid; r < n; r += c.nthreads) y[r] += rhs2[r]; }
-    SCP_SYNC(c);
   }
-  return 1;
 }
 
 // One full polish.  Returns 1 when the active set is stable (KKT certificate on the carried
@@ -1100,6 +1172,9 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   double* pcscore = c.wd + c.g->L.pcscore;
   double* sc3 = c.wd + c.g->L.red;          // one more reduction column (global scratch)
   const int full_rounds = 6;
+  int* ppos = c.wi + c.g->L.ppos;
+  int* pcpos = c.wi + c.g->L.pcpos;
+  int* pcown = c.wi + c.g->L.pcown;
   const int* coff = c.wi + c.g->L.coff;
   const int* cj = c.wi + c.g->L.c_j;
   const double* ceta = c.wd + c.g->L.c_eta;
@@ -1130,23 +1205,27 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
         int a2 = q & 1;
         v = vp[e]; mp = v > hi[a2] - off[e] ? 1 : (v < lo[a2] - off[e] ? -1 : 0);
       }
-      pmark[e] = mj; pmark[2 * QK + e] = mv; pmark[3 * QK + e] = mp;
-      for (int cls = 0; cls < 4; ++cls) { pdec[cls * QK + e] = pmark[cls * QK + e]; pscore[cls * QK + e] = 0.0; }
+      // the initial set enters through the same add path as later changes: marks start at 0, decisions = guess
+      pdec[e] = mj; pdec[QK + e] = pmark[QK + e]; pdec[2 * QK + e] = mv; pdec[3 * QK + e] = mp;
+      for (int cls = 0; cls < 4; ++cls) { pmark[cls * QK + e] = 0; pscore[cls * QK + e] = 1.0; ppos[cls * QK + e] = -1; }
     }
     if (use_col)
       for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
         int k = 1 + t / N, i = t - (k - 1) * N;
-        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx)
-          pcmark[sidx] = lam[((size_t)k * N + i) * N + cj[sidx]] > 0.0;
+        for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
+          pcmark[sidx] = 0; pcscore[sidx] = 1.0; pcpos[sidx] = -1;
+          pcdec[sidx] = lam[((size_t)k * N + i) * N + cj[sidx]] > 0.0;
+          pcown[sidx] = cj[sidx] > i ? k * N + i : -1;       // the i<j entry is the row's identity
+        }
       }
   }
   SCP_SYNC(c);
+  int n = polish_apply(c, g, 0, use_col, 0.0, 0.0);
+  if (n < 0) return 0;
 
   for (int round = 0; round < max_rounds; ++round) {
     c.polish_rounds++;
-    const int n = polish_compact(c, use_col);
-    if (n < 0) return 0;
-    if (n > 0 && !polish_solve(c, n, g)) return 0;
+    if (n > 0) polish_solve(c, n);
     // scatter multipliers to the dense arrays
     const double* y = c.wd + c.g->L.py;
     SCP_PHASE(c) {
@@ -1299,18 +1378,8 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
       // worst violated row and the worst wrong-sign multiplier per round, which breaks the cycles the full step can enter
       const int careful = round >= full_rounds;
       const double ta = careful ? madd * (1.0 - 1e-12) : 0.0, td = careful ? mdrop * (1.0 - 1e-12) : 0.0;
-      SCP_PHASE(c) {
-        for (int u = tid; u < 4 * QK; u += c.nthreads) {
-          const int m = pmark[u], nm = pdec[u];
-          if (nm != m && pscore[u] >= (nm != 0 ? ta : td)) pmark[u] = nm;
-        }
-        if (use_col)
-          for (int sidx = tid; sidx < c.ncand; sidx += c.nthreads) {
-            const int m = pcmark[sidx], nm = pcdec[sidx];
-            if (nm != m && pcscore[sidx] >= (nm != 0 ? ta : td)) pcmark[sidx] = nm;
-          }
-      }
-      SCP_SYNC(c);
+      n = polish_apply(c, g, n, use_col, ta, td);
+      if (n < 0) return 0;
     }
 #ifdef SCP_EMU_DEBUG
     if (changes == 0.0) fprintf(stderr, "  POLISH OK after %d rounds n=%d\n", round + 1, n);
