@@ -47,6 +47,20 @@ size_t nmat_smem_bytes(int K) {
   return b <= SMEM_NMAT_LIMIT ? b : 0;
 }
 
+// Shared-memory plan of scp_solve_kernel: base scratch, the K x K operator when it fits, the per-warp rows of
+// the fused iteration (K <= 64), then as many hot per-agent-axis arrays as fit, in order of reuse
+// (P and F are also read by the collision rows, then x and the four v arrays, rhs last).
+size_t plan_smem(int N, int K, int* hot_mask) {
+  size_t smem = SMEM_BASE + nmat_smem_bytes(K);
+  if (nmat_smem_bytes(K) && K <= 64) smem += (size_t)(SOLVE_THREADS / 32) * K * sizeof(double);
+  const size_t arr = (size_t)2 * N * K * sizeof(double);
+  int mask = 0;
+  for (int a = 0; a < 8; ++a)
+    if (smem + arr <= SMEM_TOTAL_LIMIT) { smem += arr; mask |= 1 << a; }
+  if (hot_mask) *hot_mask = mask;
+  return smem;
+}
+
 size_t slot_bytes(const scp::Layout& L) { return L.n_double * sizeof(double) + L.n_int * sizeof(int); }
 
 int validate(const scp_b200_problem* p) {
@@ -67,7 +81,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
                  const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
                  double* ws_d, int* ws_i, double* acc, double* pos, double* vel, scp_b200_record* rec,
-                 unsigned int* counter, int nmat_in_smem, int hot_in_smem) {
+                 unsigned int* counter, int nmat_in_smem, int hot_mask) {
   extern __shared__ double smem[];
   __shared__ int s_b;
   scp::Ctx c;
@@ -80,19 +94,19 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
   c.nmat = nullptr;
   c.nmat_in_smem = nmat_in_smem;
   {
+    // shared-memory plan (decided on the host, see plan_smem): [reductions | operator N | per-warp rhs rows | hot arrays]
     const size_t QK = (size_t)c.Q * c.K;
-    double* hot = smem + 4 * scp::RED + (nmat_in_smem ? (size_t)c.K * c.K : 0);
-    c.a_x = hot_in_smem ? hot + 0 * QK : c.wd + g.L.x;
-    c.a_rhs = hot_in_smem ? hot + 1 * QK : c.wd + g.L.rhs;
-    c.a_vj = hot_in_smem ? hot + 2 * QK : c.wd + g.L.vj;
-    c.a_va = hot_in_smem ? hot + 3 * QK : c.wd + g.L.va;
-    c.a_vv = hot_in_smem ? hot + 4 * QK : c.wd + g.L.vv;
-    c.a_vp = hot_in_smem ? hot + 5 * QK : c.wd + g.L.vp;
-    c.a_P = hot_in_smem ? hot + 6 * QK : c.wd + g.L.P;
-    c.a_F = hot_in_smem ? hot + 7 * QK : c.wd + g.L.F;
-    // warp-fused iteration: needs the operator and the hot arrays in shared memory and K <= 128
-    c.fused_epl = (hot_in_smem && nmat_in_smem && c.K <= 64) ? 2 : 0;
-    c.fused_rows = hot + 8 * QK;
+    double* cur = smem + 4 * scp::RED + (nmat_in_smem ? (size_t)c.K * c.K : 0);
+    c.fused_rows = cur;
+    const int fused_ok = nmat_in_smem && c.K <= 64;
+    if (fused_ok) cur += (size_t)(blockDim.x >> 5) * c.K;
+    double* glob[8] = {c.wd + g.L.P, c.wd + g.L.F, c.wd + g.L.x, c.wd + g.L.vp, c.wd + g.L.vv, c.wd + g.L.vj, c.wd + g.L.va, c.wd + g.L.rhs};
+    double* ptr[8];
+    for (int a = 0; a < 8; ++a) {
+      if (hot_mask & (1 << a)) { ptr[a] = cur; cur += QK; } else ptr[a] = glob[a];
+    }
+    c.a_P = ptr[0]; c.a_F = ptr[1]; c.a_x = ptr[2]; c.a_vp = ptr[3]; c.a_vv = ptr[4]; c.a_vj = ptr[5]; c.a_va = ptr[6]; c.a_rhs = ptr[7];
+    c.fused_epl = fused_ok ? 2 : 0;
   }
   for (;;) {
     if (threadIdx.x == 0) s_b = (int)atomicAdd(counter, 1u);
@@ -283,9 +297,7 @@ int scp_b200_default_slots(const scp_b200_problem* prob) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
-  size_t smem = SMEM_BASE + nmat_smem_bytes(prob->n_steps);
-  const size_t hot = 8 * (size_t)2 * prob->n_agents * prob->n_steps * sizeof(double);
-  if (smem + hot + (size_t)(SOLVE_THREADS / 32) * prob->n_steps * sizeof(double) <= SMEM_TOTAL_LIMIT) smem += hot;
+  const size_t smem = plan_smem(prob->n_agents, prob->n_steps, nullptr);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;                        // 4 x 512 threads = the SM's 2048
@@ -317,18 +329,13 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   double* ws_d = (double*)(base + 256);
   int* ws_i = (int*)(base + 256 + g.L.n_double * sizeof(double) * (size_t)slots);
   CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
+  int hot_mask = 0;
   const size_t nm = nmat_smem_bytes(K);
-  size_t smem = SMEM_BASE + nm;
-  const size_t hot = 8 * (size_t)2 * prob->n_agents * K * sizeof(double);
-  const int hot_in_smem = (smem + hot + (size_t)(SOLVE_THREADS / 32) * K * sizeof(double) <= SMEM_TOTAL_LIMIT) ? 1 : 0;
-  if (hot_in_smem) smem += hot;
-  const size_t fused_rows = (size_t)(SOLVE_THREADS / 32) * K * sizeof(double);
-  if (hot_in_smem && smem + fused_rows <= SMEM_TOTAL_LIMIT) smem += fused_rows;
-  else if (hot_in_smem) return fail(3, "internal: shared memory plan");
+  const size_t smem = plan_smem(prob->n_agents, K, &hot_mask);
   CUDA_OK(cudaFuncSetAttribute(scp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = B < slots ? B : slots;
   scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
-                                                        d_vel, d_records, counter, nm ? 1 : 0, hot_in_smem);
+                                                        d_vel, d_records, counter, nm ? 1 : 0, hot_mask);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

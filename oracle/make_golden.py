@@ -31,7 +31,7 @@ CASES = [  # name, N, T, h, R, space, seed (None: explicit positions)
     ("n10_s2", 10, 10.0, 0.2, 0.8, [0, 0, 20, 20], 2),
     ("n15_s2", 15, 10.0, 0.2, 0.8, [0, 0, 20, 20], 2),
     ("n25_s3", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 3),
-    ("n25_s10000", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 10000),
+    ("n25_s10003", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 10003),
 ]
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -56,8 +56,10 @@ def run_reference(ref, N, T, h, R, space, p0, pf, overrides):
 def main(only=None):
     ref = ref_loader.load_reference()
     gen = ref.scenarios.position_generator.generate_positions
-    truth = dict(eps_abs=1e-5, eps_rel=1e-5, max_iter=200000, certify=True)
     for name, N, T, h, R, space, seed in CASES:
+        # the certificate, not the ADMM tolerance, makes the result exact; larger cases start the refinement earlier
+        eps = 1e-5 if N < 15 else 1e-3
+        truth = dict(eps_abs=eps, eps_rel=eps, max_iter=200000, certify=True)
         if only and name not in only:
             continue
         path = os.path.join(OUT, f"{name}.npz")
