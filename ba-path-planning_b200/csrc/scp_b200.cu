@@ -38,7 +38,8 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int SOLVE_THREADS = 512;
-constexpr size_t SMEM_BASE = 4 * scp::RED * sizeof(double);
+constexpr size_t SMEM_BASE = (4 * scp::RED + scp::SH_EXTRA) * sizeof(double);   // scp::sh_doubles(RED)
+constexpr size_t TEAM_SCRATCH_BYTES = (size_t)24 << 20;   // team-wide reduction columns for the cooperative kernel
 constexpr size_t SMEM_NMAT_LIMIT = 96 * 1024;
 constexpr size_t SMEM_TOTAL_LIMIT = 227 * 1024;
 
@@ -86,6 +87,7 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
   __shared__ int s_b;
   scp::Ctx c;
   c.nthreads = blockDim.x;
+  c.team = 1; c.tid0 = 0; c.np = blockDim.x < 512 ? blockDim.x : 512; c.rs = scp::RED; c.sh = smem;
   c.N = g.pb.n_agents; c.K = g.pb.n_steps; c.Q = 2 * c.N;
   c.g = &g;
   c.wd = ws_d + (size_t)blockIdx.x * g.L.n_double;
@@ -96,7 +98,7 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
   {
     // shared-memory plan (decided on the host, see plan_smem): [reductions | operator N | per-warp rhs rows | hot arrays]
     const size_t QK = (size_t)c.Q * c.K;
-    double* cur = smem + 4 * scp::RED + (nmat_in_smem ? (size_t)c.K * c.K : 0);
+    double* cur = smem + scp::sh_doubles(scp::RED) + (nmat_in_smem ? (size_t)c.K * c.K : 0);
     c.fused_rows = cur;
     const int fused_ok = nmat_in_smem && c.K <= 64;
     if (fused_ok) cur += (size_t)(blockDim.x >> 5) * c.K;
@@ -118,6 +120,37 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
     scp::solve_scenario(c);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------- team kernel
+// One large scenario at a time solved by the WHOLE cooperative grid (one CTA per SM): the same phase
+// code, with team-global thread ids, grid-wide barriers and the reduction columns in global memory.
+// Used when there are too few scenarios to fill the GPU with one CTA each (config 3: one 200-agent scenario).
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+scp_solve_team_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
+                      const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
+                      double* ws_d, int* ws_i, double* team_scratch, double* acc, double* pos, double* vel,
+                      scp_b200_record* rec) {
+  extern __shared__ double smem[];
+  scp::Ctx c;
+  c.nthreads = gridDim.x * blockDim.x;
+  c.team = gridDim.x; c.tid0 = blockIdx.x * blockDim.x; c.np = 512; c.rs = c.nthreads; c.sh = team_scratch;
+  c.N = g.pb.n_agents; c.K = g.pb.n_steps; c.Q = 2 * c.N;
+  c.g = &g;
+  c.wd = ws_d; c.wi = ws_i;
+  c.sm = smem;
+  c.nmat = nullptr; c.nmat_in_smem = 0;
+  c.fused_epl = 0; c.fused_rows = nullptr;
+  c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F; c.a_x = c.wd + g.L.x; c.a_vp = c.wd + g.L.vp;
+  c.a_vv = c.wd + g.L.vv; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va; c.a_rhs = c.wd + g.L.rhs;
+  for (int b = 0; b < B; ++b) {
+    const size_t s2 = (size_t)b * c.N * 2, s3 = (size_t)b * c.N * c.K * 2;
+    c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
+    c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
+    scp::solve_scenario(c);
+    scp_team_sync(c.team);
   }
 }
 
@@ -290,7 +323,7 @@ int scp_b200_build_tables(const scp_b200_problem* prob, void* d_tables, void* st
 
 size_t scp_b200_workspace_bytes(const scp_b200_problem* prob, int slots) {
   scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
-  return slot_bytes(L) * (size_t)slots + 256;
+  return slot_bytes(L) * (size_t)slots + 256 + TEAM_SCRATCH_BYTES;
 }
 
 int scp_b200_default_slots(const scp_b200_problem* prob) {
@@ -321,7 +354,7 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   const double* tb = (const double*)d_tables;
   g.tb.B1 = tb; g.tb.B2 = tb + (size_t)K * K; g.tb.rj = tb + 2 * (size_t)K * K;
   g.tb.ra = g.tb.rj + K; g.tb.rv = g.tb.ra + K; g.tb.rp = g.tb.rv + K; g.tb.rc = g.tb.rp + K;
-  const size_t need = slot_bytes(g.L) * (size_t)slots + 256;
+  const size_t need = slot_bytes(g.L) * (size_t)slots + 256 + TEAM_SCRATCH_BYTES;
   if (workspace_bytes < need) return fail(2, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)d_workspace;
@@ -333,9 +366,23 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   const size_t nm = nmat_smem_bytes(K);
   const size_t smem = plan_smem(prob->n_agents, K, &hot_mask);
   CUDA_OK(cudaFuncSetAttribute(scp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = B < slots ? B : slots;
-  scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
-                                                        d_vel, d_records, counter, nm ? 1 : 0, hot_mask);
+  // few large scenarios: one scenario at a time on the whole GPU (cooperative grid); otherwise one CTA each
+  int dev = 0, sms = 148, coop = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  const bool team_mode = coop && prob->team_mode != 1 && (prob->team_mode == 2 || (B <= 8 && (size_t)2 * prob->n_agents * K >= 8192));
+  if (team_mode) {
+    double* team_scratch = (double*)(base + 256 + slot_bytes(g.L) * (size_t)slots);
+    if (scp::sh_doubles((size_t)sms * SOLVE_THREADS) * sizeof(double) > TEAM_SCRATCH_BYTES) return fail(3, "team scratch too small");
+    void* args[] = {(void*)&g, (void*)&B, (void*)&d_p0, (void*)&d_v0, (void*)&d_pf, (void*)&d_vf, (void*)&ws_d, (void*)&ws_i,
+                    (void*)&team_scratch, (void*)&d_acc, (void*)&d_pos, (void*)&d_vel, (void*)&d_records};
+    CUDA_OK(cudaLaunchCooperativeKernel((const void*)scp_solve_team_kernel, dim3(sms), dim3(SOLVE_THREADS), args, 1024, st));
+  } else {
+    const int grid = B < slots ? B : slots;
+    scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
+                                                          d_vel, d_records, counter, nm ? 1 : 0, hot_mask);
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -26,6 +26,6 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->polish_first_eps = 5e-2;
   p->polish_stage_factor = 0.3;
   p->polish_rounds = 40;
-  p->reserved0 = 0;
+  p->team_mode = 0;
 }
 #endif

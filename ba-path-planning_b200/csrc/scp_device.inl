@@ -52,16 +52,30 @@
 #else
 #define SCP_CLOCK() clock64()
 #define SCP_DEV __device__ __forceinline__
-#define SCP_PHASE(c) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
-#define SCP_SYNC(c) __syncthreads()
+#define SCP_PHASE(c) for (int tid = (c).tid0 + threadIdx.x, _once = 1; _once; _once = 0)
+#define SCP_SYNC(c) scp_team_sync((c).team)
 #define SCP_FMAX(a, b) fmax(a, b)
 #define SCP_FMIN(a, b) fmin(a, b)
+#endif
+
+#ifndef SCP_EMU
+#include <cooperative_groups.h>
+// Barrier of the team that solves one scenario: the CTA (team of 1) or the whole cooperative grid.
+__device__ __forceinline__ void scp_team_sync(int team) {
+  if (team > 1) cooperative_groups::this_grid().sync(); else __syncthreads();
+}
 #endif
 
 namespace scp {
 
 constexpr int CH = 8;           // scan chunk length
-constexpr int RED = 1024;       // reduction scratch entries (>= max threads)
+constexpr int RED = 1024;       // reduction column stride for a one-CTA team (>= its threads)
+// team scratch `sh`: 4 reduction columns of stride rs | 16 misc | 1056 second-level reduction
+constexpr int SH_EXTRA = 1072;
+#ifndef SCP_EMU
+__host__ __device__
+#endif
+inline size_t sh_doubles(size_t rs) { return 4 * rs + SH_EXTRA; }
 
 struct Tables {                 // constant per (K, h, weights); unit rho
   const double* B1;             // K*K  D'RjD + Ra + V'RvV + S'RpS
@@ -129,7 +143,11 @@ struct Params {                 // one per launch (kernel parameter / constant b
 };
 
 struct Ctx {
-  int nthreads;
+  int nthreads;                 // threads of the team solving this scenario
+  int team, tid0;               // CTAs in the team, first team-thread id of this CTA
+  int np;                       // workers of the serial-prefix phases (<= 512)
+  int rs;                       // stride of the reduction columns in `sh` (>= nthreads)
+  double* sh;                   // scratch visible to the whole team: shared memory (team of 1) or global
   int N, K, Q;                  // Q = 2N agent-axes
   const Params* g;
   double* wd;                   // slot scratch (doubles)
@@ -155,19 +173,29 @@ struct Ctx {
 // ------------------------------------------------------------------ reductions
 // Phase-style block reductions over a value every thread contributes.
 // kind 0: max, 1: sum.  Result returned to all threads.
-#define SCP_REDUCE_BEGIN(c, slot) double* _red = (c).sm + (slot) * RED
 SCP_DEV double reduce_finish(Ctx& c, int slot, int kind) {
-  double* red = c.sm + slot * RED;
+  // every team thread has written red[tid]; two strided levels (<= 1024, then 32), result to all threads
+  double* red = c.sh + (size_t)slot * c.rs;
+  double* aux = c.sh + (size_t)4 * c.rs + 16;          // 1024 + 32
+  const int n1 = c.nthreads < 1024 ? c.nthreads : 1024;
+  SCP_PHASE(c) {
+    if (tid < n1) {
+      double a = kind ? 0.0 : -INFINITY;
+      for (int e = tid; e < c.nthreads; e += n1) a = kind ? a + red[e] : SCP_FMAX(a, red[e]);
+      aux[tid] = a;
+    }
+  }
+  SCP_SYNC(c);
   SCP_PHASE(c) {
     if (tid < 32) {
       double a = kind ? 0.0 : -INFINITY;
-      for (int e = tid; e < c.nthreads; e += 32) a = kind ? a + red[e] : SCP_FMAX(a, red[e]);
-      red[RED - 32 + tid] = a;   // nthreads <= RED - 32
+      for (int e = tid; e < n1; e += 32) a = kind ? a + aux[e] : SCP_FMAX(a, aux[e]);
+      aux[1024 + tid] = a;
     }
   }
   SCP_SYNC(c);
   double r = kind ? 0.0 : -INFINITY;
-  for (int e = 0; e < 32; ++e) r = kind ? r + red[RED - 32 + e] : SCP_FMAX(r, red[RED - 32 + e]);
+  for (int e = 0; e < 32; ++e) r = kind ? r + aux[1024 + e] : SCP_FMAX(r, aux[1024 + e]);
   SCP_SYNC(c);
   return r;
 }
@@ -213,9 +241,9 @@ SCP_DEV void factor_operator(Ctx& c) {
   double* M = c.wd + c.g->L.Minv;
   double* N0 = c.wd + c.g->L.N0;
   double* Qm = c.wd + c.g->L.Qm;
-  double* colb = c.sm;             // K  (K <= RED assumed for the scratch; checked on host)
-  double* rowb = c.sm + RED;       // K
-  double* mc = c.sm + 2 * RED;     // 2K : Minv C'
+  double* colb = c.sh;             // K  (K <= RED assumed for the scratch; checked on host)
+  double* rowb = c.sh + c.rs;      // K
+  double* mc = c.sh + 2 * (size_t)c.rs;   // 2K : Minv C'
   const double rho = c.rho, sig = c.g->pb.sigma, cp = (double)c.copies;
   const double h = c.g->pb.time_step;
   SCP_PHASE(c) {
@@ -270,7 +298,7 @@ SCP_DEV void factor_operator(Ctx& c) {
       N0[2 * k] = n0; N0[2 * k + 1] = n1;          // N0 = mc G
       Qm[k] = n0; Qm[K + k] = n1;                  // Qm = G mc' (G symmetric)
     }
-    if (tid == 0) { c.sm[3 * RED + 0] = g00; c.sm[3 * RED + 1] = g01; c.sm[3 * RED + 2] = g11; }
+    if (tid == 0) { double* gg = c.sh + 4 * (size_t)c.rs; gg[0] = g00; gg[1] = g01; gg[2] = g11; }
   }
   SCP_SYNC(c);
   SCP_PHASE(c) {
@@ -281,7 +309,7 @@ SCP_DEV void factor_operator(Ctx& c) {
   }
   SCP_SYNC(c);
   if (c.nmat_in_smem) {
-    double* dst = c.sm + 4 * RED;
+    double* dst = c.sm + sh_doubles(RED);
     SCP_PHASE(c) { for (int e = tid; e < K * K; e += c.nthreads) dst[e] = M[e]; }
     SCP_SYNC(c);
     c.nmat = dst;
@@ -445,7 +473,8 @@ SCP_DEV void x_update(Ctx& c, int want_mu) {
       x[e] = a;
     }
     if (want_mu) {
-      const double g00 = c.sm[3 * RED + 0], g01 = c.sm[3 * RED + 1], g11 = c.sm[3 * RED + 2];
+      const double* gg = c.sh + 4 * (size_t)c.rs;
+      const double g00 = gg[0], g01 = gg[1], g11 = gg[2];
       for (int t = tid; t < 2 * c.Q; t += c.nthreads) {
         int q = t >> 1, ee = t & 1;
         const double* r = rhs + (size_t)q * K;
@@ -573,13 +602,21 @@ __device__ __forceinline__ void admm_iter_fused(Ctx& c, double* rhs_rows /* nwar
       const int k = lane + 32 * e;
       xn[e] = (k < K) ? N0[2 * k] * d0 + N0[2 * k + 1] * d1 : 0.0;
     }
-    for (int j = 0; j < K; ++j) {
-      const double r = myrhs[j];
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const int k = lane + 32 * e;
-        if (k < K) xn[e] += Nm[j * K + k] * r;
+    {
+      // column walk of the symmetric operator: lane owns columns lane, lane+32 (clamped, masked at the end)
+      const double* np0 = Nm + lane;
+      const double* np1 = Nm + ((lane + 32 < K) ? lane + 32 : lane);
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      int j = 0;
+      for (; j + 1 < K; j += 2) {
+        const double r0 = myrhs[j], r1 = myrhs[j + 1];
+        a0 += np0[0] * r0; a1 += np1[0] * r0;
+        b0 += np0[K] * r1; b1 += np1[K] * r1;
+        np0 += 2 * K; np1 += 2 * K;
       }
+      if (j < K) { const double r0 = myrhs[j]; a0 += np0[0] * r0; a1 += np1[0] * r0; }
+      if (lane < K) xn[0] += a0 + b0;
+      if (EPL > 1 && lane + 32 < K) xn[1] += a1 + b1;
     }
     __syncwarp();
     // ---- forward rows and v update
@@ -630,7 +667,7 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
   double* lam = c.wd + c.g->L.lam;        // dense [k][i][j]; the two owners keep identical copies
   double* dlam = c.wd + c.g->L.plam;      // last multiplier step per carried entry (check iterations)
   double* FD = c.wd + c.g->L.Pt;          // sum_j dlam eta (check iterations; Pt is free outside the polish)
-  double* red = c.sm;
+  double* red = c.sh;
   const double rho = c.rho;
   SCP_PHASE(c) {
     double worst = 0.0;
@@ -719,24 +756,29 @@ SCP_DEV void build_candidates(Ctx& c) {
   }
   SCP_SYNC(c);
   // exclusive scan of cnt -> coff (two-level, phase style), max -> copies
-  const int per = (total + c.nthreads - 1) / c.nthreads;
-  int* part = (int*)(c.sm + 2 * RED);        // nthreads ints
-  int* pmax = part + RED;
+  const int np = c.np;
+  const int per = (total + np - 1) / np;
+  int* part = (int*)(c.sh + 2 * (size_t)c.rs);        // np ints
+  int* pmax = part + 512;
   SCP_PHASE(c) {
-    int s = 0, m = 0;
-    for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { s += cnt[e]; m = cnt[e] > m ? cnt[e] : m; }
-    part[tid] = s; pmax[tid] = m;
+    if (tid < np) {
+      int s = 0, m = 0;
+      for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { s += cnt[e]; m = cnt[e] > m ? cnt[e] : m; }
+      part[tid] = s; pmax[tid] = m;
+    }
   }
   SCP_SYNC(c);
   SCP_PHASE(c) {
-    int base = 0;
-    for (int e = 0; e < tid; ++e) base += part[e];
-    for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { coff[e] = base; base += cnt[e]; }
-    if (tid == c.nthreads - 1) coff[total] = base;
+    if (tid < np) {
+      int base = 0;
+      for (int e = 0; e < tid; ++e) base += part[e];
+      for (int e = tid * per; e < total && e < (tid + 1) * per; ++e) { coff[e] = base; base += cnt[e]; }
+      if (tid == np - 1) coff[total] = base;
+    }
   }
   SCP_SYNC(c);
   int mx = 0;
-  for (int e = 0; e < c.nthreads; ++e) mx = pmax[e] > mx ? pmax[e] : mx;
+  for (int e = 0; e < np; ++e) mx = pmax[e] > mx ? pmax[e] : mx;
   c.copies = mx;
   c.ncand = coff[total];
   SCP_SYNC(c);
@@ -767,7 +809,7 @@ SCP_DEV int verify_rows(Ctx& c, double tol) {
   unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
   double* lam = c.wd + c.g->L.lam;
   const double R = c.g->pb.min_distance;
-  double* red = c.sm;
+  double* red = c.sh;
   SCP_PHASE(c) {
     double bad = 0.0;
     for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
@@ -800,7 +842,7 @@ SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, doubl
   const int K = c.K, N = c.N;
   const double* P = c.a_P;
   const double thr = c.g->pb.min_distance - c.g->pb.feas_margin;
-  double* red = c.sm;            // slot 0: -min distance ; slot 1: -(first row index) ; slot 2: dist of it
+  double* red = c.sh;            // slot 0: -min distance ; slot 1: -(first row index) ; slot 2: dist of it
   const long long npairs = (long long)N * (N - 1) / 2;
   SCP_PHASE(c) {
     double mn = INFINITY, fr = INFINITY, fd = 0.0;
@@ -818,12 +860,14 @@ SCP_DEV void gate_and_minsep(Ctx& c, double* minsep, long long* first_row, doubl
         }
       }
     }
-    red[tid] = -mn; red[RED + tid] = -fr; red[2 * RED + tid] = fd;
+    red[tid] = -mn; red[c.rs + tid] = -fr; red[2 * (size_t)c.rs + tid] = fd;
   }
   SCP_SYNC(c);
-  // first row: max of -fr, carrying its distance
-  double best = -INFINITY, bd = 0.0;
-  for (int e = 0; e < c.nthreads; ++e) if (red[RED + e] > best) { best = red[RED + e]; bd = red[2 * RED + e]; }
+  // first row: max of -fr, then the distance carried by the thread(s) that hold it
+  const double best = reduce_finish(c, 1, 0);
+  SCP_PHASE(c) { if (!(red[c.rs + tid] == best)) red[2 * (size_t)c.rs + tid] = -INFINITY; }
+  SCP_SYNC(c);
+  const double bd = (best == -INFINITY) ? 0.0 : reduce_finish(c, 2, 0);
   double m = reduce_finish(c, 0, 0);
   *minsep = -m;
   *first_row = (best == -INFINITY) ? -1 : (long long)(-best);
@@ -974,7 +1018,7 @@ SCP_DEV int polish_add(Ctx& c, const PGeom& g, int n) {
   double* G0 = c.wd + c.g->L.pG;
   double* gv = c.wd + c.g->L.scr;                // n+1
   double* u = gv + c.g->L.pcap;                  // n
-  double* red = c.sm;
+  double* red = c.sh;
   SCP_PHASE(c) {
     const PRow nw = load_prow(c, n);
     for (int i = tid; i <= n; i += c.nthreads) {
@@ -1066,24 +1110,25 @@ SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_
   const int* pcown = c.wi + c.g->L.pcown;
   const int* coff = c.wi + c.g->L.coff; const int* cj = c.wi + c.g->L.c_j;
   const int total = 4 * QK + (use_col ? c.ncand : 0);
-  const int per = (total + c.nthreads - 1) / c.nthreads;
-  int* part = (int*)(c.sm + 2 * RED);
+  const int np = c.np;
+  const int per = (total + np - 1) / np;
+  int* part = (int*)(c.sh + 2 * (size_t)c.rs);
   SCP_PHASE(c) {
     int cnt = 0;
-    for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
+    if (tid < np) for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
       if (u < 4 * QK) { const int nm = pdec[u]; cnt += (nm != pmark[u] && pscore[u] >= (nm != 0 ? thr_add : thr_drop)); }
       else { const int sidx = u - 4 * QK, nm = pcdec[sidx]; cnt += (pcown[sidx] >= 0 && nm != pcmark[sidx] && pcscore[sidx] >= (nm != 0 ? thr_add : thr_drop)); }
     }
-    part[tid] = cnt;
+    if (tid < np) part[tid] = cnt;
   }
   SCP_SYNC(c);
   int nchg = 0;
-  for (int e = 0; e < c.nthreads; ++e) nchg += part[e];
+  for (int e = 0; e < np; ++e) nchg += part[e];
   const int chg_cap = c.g->L.pcap;
   SCP_PHASE(c) {
     int base = 0;
-    for (int e = 0; e < tid; ++e) base += part[e];
-    for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
+    if (tid < np) for (int e = 0; e < tid; ++e) base += part[e];
+    if (tid < np) for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
       int hit;
       if (u < 4 * QK) { const int nm = pdec[u]; hit = (nm != pmark[u] && pscore[u] >= (nm != 0 ? thr_add : thr_drop)); }
       else { const int sidx = u - 4 * QK, nm = pcdec[sidx]; hit = (pcown[sidx] >= 0 && nm != pcmark[sidx] && pcscore[sidx] >= (nm != 0 ? thr_add : thr_drop)); }
@@ -1170,7 +1215,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   int* pcdec = c.wi + c.g->L.pcdec;
   double* pscore = c.wd + c.g->L.pscore;
   double* pcscore = c.wd + c.g->L.pcscore;
-  double* sc3 = c.wd + c.g->L.red;          // one more reduction column (global scratch)
+  double* sc3 = c.sh + 3 * (size_t)c.rs;     // fourth reduction column
   const int full_rounds = 6;
   int* ppos = c.wi + c.g->L.ppos;
   int* pcpos = c.wi + c.g->L.pcpos;
@@ -1185,7 +1230,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   double *yj = c.wd + c.g->L.yj, *ya = c.wd + c.g->L.ya, *yv = c.wd + c.g->L.yv, *yp = c.wd + c.g->L.yp;
   double *off = c.wd + c.g->L.off, *deq = c.wd + c.g->L.deq;
   double *xt = c.wd + c.g->L.xt, *Pt = c.wd + c.g->L.Pt, *w = c.a_rhs, *FY = c.wd + c.g->L.FY;
-  double* red = c.sm;
+  double* red = c.sh;
   const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
   const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
   const int use_col = with_collisions && c.ncand > 0;
@@ -1332,7 +1377,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
         }
         if (ch == 0) Pt[q * K] = c.p0[q];
       }
-      red[tid] = changes; red[RED + tid] = broken; red[2 * RED + tid] = madd;
+      red[tid] = changes; red[c.rs + tid] = broken; red[2 * (size_t)c.rs + tid] = madd;
       sc3[tid] = mdrop;
     }
     SCP_SYNC(c);
@@ -1359,7 +1404,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
             if (nm != m) { if (j > i) ch2 += 1.0; if (nm) ma2 = SCP_FMAX(ma2, score); else md2 = SCP_FMAX(md2, score); }
           }
         }
-        red[tid] = ch2; red[RED + tid] = br2; red[2 * RED + tid] = ma2; sc3[tid] = md2;
+        red[tid] = ch2; red[c.rs + tid] = br2; red[2 * (size_t)c.rs + tid] = ma2; sc3[tid] = md2;
       }
       SCP_SYNC(c);
       changes += reduce_finish(c, 0, 1);
@@ -1438,7 +1483,7 @@ SCP_DEV int primal_infeasible(Ctx& c, int with_collisions) {
   double* w = c.a_rhs;
   double* dmu = c.wd + c.g->L.scr;            // 2 per q
   const double* deq = c.wd + c.g->L.deq;
-  double* red = c.sm;
+  double* red = c.sh;
   SCP_PHASE(c) {
     for (int q = tid; q < c.Q; q += c.nthreads) {
       double a0 = 0, a1 = 0;
@@ -1470,7 +1515,7 @@ SCP_DEV int primal_infeasible(Ctx& c, int with_collisions) {
       }
       if (k == 0) sup += deq[2 * q] * dmu[2 * q] + deq[2 * q + 1] * dmu[2 * q + 1];
     }
-    red[tid] = gn; red[RED + tid] = yn; red[2 * RED + tid] = sup;
+    red[tid] = gn; red[c.rs + tid] = yn; red[2 * (size_t)c.rs + tid] = sup;
   }
   SCP_SYNC(c);
   double gn = reduce_finish(c, 0, 0), yn = reduce_finish(c, 1, 0), sup = reduce_finish(c, 2, 1);
@@ -1495,7 +1540,7 @@ SCP_DEV int primal_infeasible(Ctx& c, int with_collisions) {
           sup2 += (cb[sidx] - offi) * (-dl);         // l dy-  (row coordinates)
         }
       }
-      red[tid] = yn2; red[RED + tid] = sup2;
+      red[tid] = yn2; red[c.rs + tid] = sup2;
     }
     SCP_SYNC(c);
     yn = SCP_FMAX(yn, reduce_finish(c, 0, 0));
@@ -1517,7 +1562,7 @@ SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double
   const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
   const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
   const double h = c.g->pb.time_step;
-  double* red = c.sm;
+  double* red = c.sh;
   SCP_PHASE(c) {
     double n = 0.0, sidsum = 0.0;
     for (int e = tid; e < QK; e += c.nthreads) {
@@ -1548,7 +1593,7 @@ SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double
         }
       }
     }
-    red[tid] = n; red[RED + tid] = sidsum;
+    red[tid] = n; red[c.rs + tid] = sidsum;
   }
   SCP_SYNC(c);
   *count = reduce_finish(c, 0, 1);
@@ -1561,7 +1606,7 @@ struct AdmmOut { int iters; int solved; int certified; int infeasible; int polis
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
   AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
-  double* red = c.sm;
+  double* red = c.sh;
   double* x = c.a_x;
   if (!keep_state) forward_rows(c, 0);
   const int check = c.g->pb.check_every;
@@ -1609,7 +1654,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
           nr = SCP_FMAX(nr, SCP_FMAX(fabs(aj), SCP_FMAX(fabs(velrow[e]), fabs(posrow[e]))));
         }
       }
-      red[tid] = pr; red[RED + tid] = nr;
+      red[tid] = pr; red[c.rs + tid] = nr;
     }
     SCP_SYNC(c);
     double pri = reduce_finish(c, 0, 0);
@@ -1623,7 +1668,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
         du = SCP_FMAX(du, fabs(dres[e]));
         nd = SCP_FMAX(nd, SCP_FMAX(fabs(2.0 * x[e]), fabs(dres[e] - 2.0 * x[e])));
       }
-      red[tid] = du; red[RED + tid] = nd;
+      red[tid] = du; red[c.rs + tid] = nd;
     }
     SCP_SYNC(c);
     double dua = reduce_finish(c, 0, 0);
@@ -1711,7 +1756,7 @@ SCP_DEV void write_outputs(Ctx& c) {
 // ------------------------------------------------------------------ the SCP loop
 SCP_DEV void solve_scenario(Ctx& c) {
   const int K = c.K, N = c.N;
-  double* red = c.sm;
+  double* red = c.sh;
   scp_b200_record r;
   r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
   r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
@@ -1779,7 +1824,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
     SCP_PHASE(c) {
       double s0 = 0, s1 = 0;
       for (int e = tid; e < c.Q * K; e += c.nthreads) { double d = x[e] - xprev[e]; s0 += d * d; s1 += xprev[e] * xprev[e]; }
-      red[tid] = s0; red[RED + tid] = s1;
+      red[tid] = s0; red[c.rs + tid] = s1;
     }
     SCP_SYNC(c);
     double dn = reduce_finish(c, 0, 1), pn = reduce_finish(c, 1, 1);

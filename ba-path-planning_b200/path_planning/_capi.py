@@ -48,7 +48,7 @@ class Problem(C.Structure):
         ("polish_first_eps", C.c_double),
         ("polish_stage_factor", C.c_double),
         ("polish_rounds", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("team_mode", C.c_int32),
     ]
 
 

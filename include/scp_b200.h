@@ -60,7 +60,7 @@ typedef struct scp_b200_problem {
   double polish_first_eps; /* residual gate: polish is tried once pri,dua <= gate*(1+norm) and the active set has settled */
   double polish_stage_factor; /* reserved */
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */
-  int32_t reserved0;
+  int32_t team_mode;       /* 0 auto, 1 one CTA per scenario, 2 whole cooperative grid per scenario */
 } scp_b200_problem;
 
 /* Per-scenario result record (device or host array of B records). */

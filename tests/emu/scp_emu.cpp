@@ -26,10 +26,11 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
   std::vector<double> wd(g.L.n_double, std::nan(""));   // poisoned: the GPU scratch is uninitialised too
   std::vector<int> wi(g.L.n_int);
   { unsigned st = 12345u; for (auto& v : wi) { st = st * 1664525u + 1013904223u; v = (int)(st >> 4) - (1 << 26); } }   // garbage like GPU scratch
-  std::vector<double> sm(4 * RED + (size_t)K * K, 0.0);
+  std::vector<double> sm(sh_doubles(RED) + (size_t)K * K, 0.0);
   for (int b = 0; b < B; ++b) {
     Ctx c;
     c.nthreads = nthreads; c.N = N; c.K = K; c.Q = 2 * N; c.g = &g;
+    c.team = 1; c.tid0 = 0; c.np = nthreads < 512 ? nthreads : 512; c.rs = RED; c.sh = sm.data();
     c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1; c.fused_epl = 0; c.fused_rows = nullptr;
     c.a_x = c.wd + g.L.x; c.a_rhs = c.wd + g.L.rhs; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va;
     c.a_vv = c.wd + g.L.vv; c.a_vp = c.wd + g.L.vp; c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F;

@@ -183,6 +183,29 @@ def test_solve_matches_golden(torch_cuda, lib, path):
           f"ADMM iterations {r['admm_iterations']}")
 
 
+@pytest.mark.parametrize("name", ["n10_s2.npz", "n25_s3.npz"])
+def test_team_mode_matches_golden(torch_cuda, lib, name):
+    """Whole-grid cooperative kernel (the path large single scenarios take) forced on a small fixture."""
+    import os
+
+    from conftest import GOLDEN
+
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    acc, pos, vel, recs = _solve_host(lib, g["p0"], g["pf"], float(g["T"]), float(g["h"]), float(g["R"]), list(g["space"]),
+                                      team_mode=2)
+    r = recs[0]
+    assert r["status"] == 0 and r["scp_iterations"] == int(g["iterations"])
+    assert np.linalg.norm(pos[0] - g["positions"]) / np.linalg.norm(g["positions"]) <= POS_TOL
+    assert abs(r["objective"] - float(g["objective"])) <= OBJ_TOL * float(g["objective"])
+    acc1, _, _, recs1 = _solve_host(lib, g["p0"], g["pf"], float(g["T"]), float(g["h"]), float(g["R"]), list(g["space"]),
+                                    team_mode=1)
+    assert recs1[0]["scp_iterations"] == r["scp_iterations"]
+    assert np.abs(acc1 - acc).max() <= 1e-9 * max(1.0, np.abs(acc).max())
+
+
 def test_solve_matches_live_oracle(torch_cuda, lib, truth_mode):
     """Seeded scenarios not in the fixtures, oracle run here (seconds)."""
     from oracle import scenarios, scp_oracle
