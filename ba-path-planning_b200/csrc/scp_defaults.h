@@ -25,6 +25,8 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->verify_tol = 1e-6;
   p->polish_first_eps = 5e-2;
   p->polish_stage_factor = 0.3;
+  p->stall_window = 500;
+  p->reserved3 = 0;
   p->polish_rounds = 40;
   p->team_mode = 0;
 }

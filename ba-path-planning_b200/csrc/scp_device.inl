@@ -1611,6 +1611,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
   if (!keep_state) forward_rows(c, 0);
   const int check = c.g->pb.check_every;
   double prev_sc = -1.0, prev_ss = -1.0, fail_sc = -2.0, fail_ss = -2.0;
+  int it_mark = 0; double pri_mark = INFINITY;
   for (int it = 1; it <= maxit; ++it) {
     const int chk = (it % check == 0) || it == maxit;
 #ifndef SCP_EMU
@@ -1677,6 +1678,13 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
     if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
     if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
+    // stalled: the primal residual is still far from feasibility and has not dropped by 20 % over the last
+    // `stall_window` iterations -- the signature of an infeasible subproblem long before the certificate's
+    // direction test converges.  The iterate is kept, as for an iteration-limit exit (scp.py:446-449).
+    if (c.g->pb.stall_window > 0 && it - it_mark >= c.g->pb.stall_window) {
+      if (pri > 1e-3 * (1.0 + npri) && pri > 0.8 * pri_mark) { o.infeasible = 2; break; }
+      it_mark = it; pri_mark = pri;
+    }
     if (c.g->pb.polish) {
       // polish when the active set has not changed between two consecutive checks (and differs from the
       // last set that failed), once the iterate is inside a loose residual gate
@@ -1816,7 +1824,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
       r.rebuilds++;
     }
     if (!a.solved) r.qp_unsolved++;
-    r.qp_infeasible += a.infeasible;
+    r.qp_infeasible += (a.infeasible != 0);
     r.polish_ok += a.certified;
     r.polish_attempts += a.polish_attempts;
     r.pri_res = a.pri; r.dua_res = a.dua;

@@ -47,6 +47,8 @@ class Problem(C.Structure):
         ("verify_tol", C.c_double),
         ("polish_first_eps", C.c_double),
         ("polish_stage_factor", C.c_double),
+        ("stall_window", C.c_int32),
+        ("reserved3", C.c_int32),
         ("polish_rounds", C.c_int32),
         ("team_mode", C.c_int32),
     ]

@@ -59,6 +59,8 @@ typedef struct scp_b200_problem {
   double verify_tol;       /* dropped rows must hold to this tolerance */
   double polish_first_eps; /* residual gate: polish is tried once pri,dua <= gate*(1+norm) and the active set has settled */
   double polish_stage_factor; /* reserved */
+  int32_t stall_window;    /* give up on a subproblem whose primal residual stalls over this many iterations (0: off) */
+  int32_t reserved3;
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */
   int32_t team_mode;       /* 0 auto, 1 one CTA per scenario, 2 whole cooperative grid per scenario */
 } scp_b200_problem;
