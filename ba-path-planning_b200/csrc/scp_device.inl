@@ -711,7 +711,7 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
 //   direction (+-1, 0) and dist := 1 (the reference draws a random one, :503-507).
 // verify_rows: every row of the full QP evaluated at the current positions; a
 //   violated row that is not carried is flagged (multiplier 0) and counted.
-SCP_DEV void mark_near_rows(Ctx& c, double margin) {
+SCP_DEV void mark_near_rows(Ctx& c, double margin, int keep_lam) {
   const int K = c.K, N = c.N;
   const double* Pb = c.wd + c.g->L.Pbar;
   unsigned char* flags = (unsigned char*)(c.wi + c.g->L.flags);
@@ -727,8 +727,9 @@ SCP_DEV void mark_near_rows(Ctx& c, double margin) {
       for (int j = 0; j < N; ++j) {
         double dx = pix - Pb[(2 * j) * K + k], dy = piy - Pb[(2 * j + 1) * K + k];
         int near = (k >= 1) && (j != i) && (dx * dx + dy * dy < r2);
+        // warm duals: a row carried by the previous subproblem keeps its multiplier (same minimiser, fewer iterations)
+        if (near && !(keep_lam && flags[(size_t)t * N + j])) lam[(size_t)t * N + j] = 0.0;
         flags[(size_t)t * N + j] = (unsigned char)near;
-        if (near) lam[(size_t)t * N + j] = 0.0;
       }
     }
     for (int e = tid; e < c.Q * K; e += c.nthreads) { F[e] = 0.0; FY[e] = 0.0; }
@@ -1609,6 +1610,15 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
   double* red = c.sh;
   double* x = c.a_x;
   if (!keep_state) forward_rows(c, 0);
+  if (c.g->pb.polish && c.g->pb.polish_first) {
+    // try the active set the state already implies (previous subproblem's multipliers with warm duals,
+    // nothing otherwise) before iterating at all
+    const long long t0 = SCP_CLOCK();
+    const int pol = polish(c, with_collisions, c.g->pb.polish_first);
+    c.t_polish += SCP_CLOCK() - t0;
+    o.polish_attempts++;
+    if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; return o; }
+  }
   const int check = c.g->pb.check_every;
   double prev_sc = -1.0, prev_ss = -1.0, fail_sc = -2.0, fail_ss = -2.0;
   int it_mark = 0; double pri_mark = INFINITY;
@@ -1806,15 +1816,16 @@ SCP_DEV void solve_scenario(Ctx& c) {
     }
     SCP_SYNC(c);
     AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.infeasible = 0; a.pri = a.dua = 0;
-    mark_near_rows(c, c.g->pb.cand_margin);
-    c.rho = c.g->pb.rho0;
-    int have_state = 0;
+    const int warm = c.g->pb.warm_duals && it > 0;     // OSQP restarts y = 0 every SCP iteration (scp.py:441-443);
+    mark_near_rows(c, c.g->pb.cand_margin, warm);      // keeping the duals changes the path, not the minimiser
+    if (!warm) c.rho = c.g->pb.rho0;
+    int have_state = 0, keep = warm;
     for (int attempt = 0;; ++attempt) {
       int old_copies = c.copies;
       build_candidates(c);
       if (c.copies > r.max_copies) r.max_copies = c.copies;
       if (!have_state || c.copies != old_copies) factor_operator(c);
-      a = solve_qp(c, 1, have_state);                  // QP #t, scp.py:155
+      a = solve_qp(c, 1, have_state || keep);          // QP #t, scp.py:155
       have_state = 1;
       r.admm_iterations += a.iters;
       r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;

@@ -46,9 +46,10 @@ class Problem(C.Structure):
         ("cand_margin", C.c_double),
         ("verify_tol", C.c_double),
         ("polish_first_eps", C.c_double),
-        ("polish_stage_factor", C.c_double),
+        ("polish_first", C.c_int32),
+        ("reserved4", C.c_int32),
         ("stall_window", C.c_int32),
-        ("reserved3", C.c_int32),
+        ("warm_duals", C.c_int32),
         ("polish_rounds", C.c_int32),
         ("team_mode", C.c_int32),
     ]

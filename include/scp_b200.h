@@ -58,9 +58,10 @@ typedef struct scp_b200_problem {
   double cand_margin;      /* collision rows kept when prev. distance < R + margin */
   double verify_tol;       /* dropped rows must hold to this tolerance */
   double polish_first_eps; /* residual gate: polish is tried once pri,dua <= gate*(1+norm) and the active set has settled */
-  double polish_stage_factor; /* reserved */
+  int32_t polish_first;    /* >0: polish attempt with this many rounds before the first ADMM iteration of a subproblem */
+  int32_t reserved4;
   int32_t stall_window;    /* give up on a subproblem whose primal residual stalls over this many iterations (0: off) */
-  int32_t reserved3;
+  int32_t warm_duals;      /* 1: keep multipliers across SCP iterations (reference/OSQP restarts from y = 0) */
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */
   int32_t team_mode;       /* 0 auto, 1 one CTA per scenario, 2 whole cooperative grid per scenario */
 } scp_b200_problem;
