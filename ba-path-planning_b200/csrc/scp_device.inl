@@ -163,6 +163,8 @@ struct Ctx {
   int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
   double* fused_rows;           // per-warp right-hand-side rows (shared)
   int polish_rounds;            // add/drop rounds over all attempts of this scenario
+  int pol_valid, pol_n, pol_use_col;   // polish list/inverse state carried between attempts on one candidate set
+  long long t_pbuild, t_psolve, t_peval, t_papply;
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   // block-uniform solver state
   double rho;
@@ -782,6 +784,7 @@ SCP_DEV void build_candidates(Ctx& c) {
   for (int e = 0; e < np; ++e) mx = pmax[e] > mx ? pmax[e] : mx;
   c.copies = mx;
   c.ncand = coff[total];
+  c.pol_valid = 0;                 // the candidate set changed: the polish list refers to the old CSR
   SCP_SYNC(c);
   SCP_PHASE(c) {
     for (int t = tid; t < total; t += c.nthreads) {
@@ -1184,7 +1187,7 @@ SCP_DEV void polish_solve(Ctx& c, int n) {
   const double* rhs = c.wd + c.g->L.prhs;
   double* y = c.wd + c.g->L.py;
   double* z = c.wd + c.g->L.scr;
-  for (int sweep = 0; sweep < 3; ++sweep) {
+  for (int sweep = 0; sweep < 2; ++sweep) {
     SCP_PHASE(c) {
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = rhs[r];
@@ -1237,12 +1240,15 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   const int use_col = with_collisions && c.ncand > 0;
   const double ptol = 1e-9, dtol = 1e-9, etol = 1e-7;
 
-  // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0
+  // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0.  The list, its inverse and the
+  // marks survive between attempts on the same candidate set, so only the difference to the new guess is applied.
+  const int fresh = !(c.pol_valid && c.pol_use_col == use_col);
+  long long tq = SCP_CLOCK();
   SCP_PHASE(c) {
     for (int e = tid; e < QK; e += c.nthreads) {
       int q = e / K, k = e - q * K;
       double v = va[e];
-      pmark[QK + e] = v > al ? 1 : (v < -al ? -1 : 0);
+      const int ma = v > al ? 1 : (v < -al ? -1 : 0);
       int mj = 0, mv = 0, mp = 0;
       if (k < K - 1) {
         v = vj[e]; mj = v > jl ? 1 : (v < -jl ? -1 : 0);
@@ -1251,27 +1257,37 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
         int a2 = q & 1;
         v = vp[e]; mp = v > hi[a2] - off[e] ? 1 : (v < lo[a2] - off[e] ? -1 : 0);
       }
-      // the initial set enters through the same add path as later changes: marks start at 0, decisions = guess
-      pdec[e] = mj; pdec[QK + e] = pmark[QK + e]; pdec[2 * QK + e] = mv; pdec[3 * QK + e] = mp;
-      for (int cls = 0; cls < 4; ++cls) { pmark[cls * QK + e] = 0; pscore[cls * QK + e] = 1.0; ppos[cls * QK + e] = -1; }
+      pdec[e] = mj; pdec[QK + e] = ma; pdec[2 * QK + e] = mv; pdec[3 * QK + e] = mp;
+      for (int cls = 0; cls < 4; ++cls) {
+        pscore[cls * QK + e] = 1.0;
+        if (fresh) { pmark[cls * QK + e] = 0; ppos[cls * QK + e] = -1; }
+      }
     }
     if (use_col)
       for (int t = tid; t < (K - 1) * N; t += c.nthreads) {
         int k = 1 + t / N, i = t - (k - 1) * N;
         for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
-          pcmark[sidx] = 0; pcscore[sidx] = 1.0; pcpos[sidx] = -1;
+          pcscore[sidx] = 1.0;
           pcdec[sidx] = lam[((size_t)k * N + i) * N + cj[sidx]] > 0.0;
-          pcown[sidx] = cj[sidx] > i ? k * N + i : -1;       // the i<j entry is the row's identity
+          if (fresh) {
+            pcmark[sidx] = 0; pcpos[sidx] = -1;
+            pcown[sidx] = cj[sidx] > i ? k * N + i : -1;     // the i<j entry is the row's identity
+          }
         }
       }
   }
   SCP_SYNC(c);
-  int n = polish_apply(c, g, 0, use_col, 0.0, 0.0);
+  int n = polish_apply(c, g, fresh ? 0 : c.pol_n, use_col, 0.0, 0.0);
+  c.t_pbuild += SCP_CLOCK() - tq;
+  c.pol_use_col = use_col; c.pol_n = n; c.pol_valid = n >= 0;
   if (n < 0) return 0;
 
   for (int round = 0; round < max_rounds; ++round) {
     c.polish_rounds++;
+    tq = SCP_CLOCK();
     if (n > 0) polish_solve(c, n);
+    c.t_psolve += SCP_CLOCK() - tq;
+    tq = SCP_CLOCK();
     // scatter multipliers to the dense arrays
     const double* y = c.wd + c.g->L.py;
     SCP_PHASE(c) {
@@ -1418,13 +1434,17 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
 #ifdef SCP_EMU_DEBUG
     if (broken > 0.0) fprintf(stderr, "  POLISH BROKEN at round %d n=%d\n", round, n);
 #endif
+    c.t_peval += SCP_CLOCK() - tq;
     if (broken > 0.0) return 0;             // active rows not met as equalities: inconsistent (infeasible) set
     if (changes > 0.0) {
       // apply the decisions: all of them in the first rounds (primal-dual active set step); afterwards only the
       // worst violated row and the worst wrong-sign multiplier per round, which breaks the cycles the full step can enter
       const int careful = round >= full_rounds;
       const double ta = careful ? madd * (1.0 - 1e-12) : 0.0, td = careful ? mdrop * (1.0 - 1e-12) : 0.0;
+      tq = SCP_CLOCK();
       n = polish_apply(c, g, n, use_col, ta, td);
+      c.t_papply += SCP_CLOCK() - tq;
+      c.pol_n = n; c.pol_valid = n >= 0;
       if (n < 0) return 0;
     }
 #ifdef SCP_EMU_DEBUG
@@ -1778,14 +1798,18 @@ SCP_DEV void solve_scenario(Ctx& c) {
   scp_b200_record r;
   r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
   r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
-  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.polish_rounds = 0; r.reserved2 = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
+  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.polish_rounds = 0; r.reserved2 = 0;
+  r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0;
+ 
+  r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
   r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
   r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
   r.cand_row_iters = 0;
   for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
 
   setup_scenario(c);
-  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0;
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0;
+  c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
   const long long t_begin = SCP_CLOCK();
   factor_operator(c);
   AdmmOut a0 = solve_qp(c, 0, 0);
@@ -1865,6 +1889,7 @@ SCP_DEV void solve_scenario(Ctx& c) {
   r.objective = reduce_finish(c, 0, 1);
   write_outputs(c);
   r.cycles_total = SCP_CLOCK() - t_begin; r.cycles_admm = c.t_admm; r.cycles_polish = c.t_polish; r.polish_rounds = c.polish_rounds;
+  r.cycles_pbuild = c.t_pbuild; r.cycles_psolve = c.t_psolve; r.cycles_peval = c.t_peval; r.cycles_papply = c.t_papply;
   SCP_PHASE(c) { if (tid == 0) *c.rec = r; }
   SCP_SYNC(c);
 }

@@ -80,6 +80,10 @@ class Record(C.Structure):
         ("cycles_polish", C.c_int64),
         ("polish_rounds", C.c_int32),
         ("reserved2", C.c_int32),
+        ("cycles_pbuild", C.c_int64),
+        ("cycles_psolve", C.c_int64),
+        ("cycles_peval", C.c_int64),
+        ("cycles_papply", C.c_int64),
         ("rel_step", C.c_double * MAX_SCP_ITER),
     ]
 
@@ -179,7 +183,8 @@ def record_to_dict(r: Record) -> dict:
         initial_feasible=bool(r.initial_feasible), admm_iterations=int(r.admm_iterations),
         qp_unsolved=int(r.qp_unsolved), rebuilds=int(r.rebuilds), max_copies=int(r.max_copies),
         first_violation=tuple(int(v) for v in r.first_violation), polish_ok=int(r.polish_ok), qp_infeasible=int(r.qp_infeasible), polish_attempts=int(r.polish_attempts),
-        cycles_total=int(r.cycles_total), cycles_admm=int(r.cycles_admm), cycles_polish=int(r.cycles_polish), polish_rounds=int(r.polish_rounds),
+        cycles_total=int(r.cycles_total), cycles_admm=int(r.cycles_admm), cycles_polish=int(r.cycles_polish), polish_rounds=int(r.polish_rounds), cycles_pbuild=int(r.cycles_pbuild), cycles_psolve=int(r.cycles_psolve),
+        cycles_peval=int(r.cycles_peval), cycles_papply=int(r.cycles_papply),
         first_violation_dist=float(r.first_violation_dist), min_separation=float(r.min_separation),
         objective=float(r.objective), pri_res=float(r.pri_res), dua_res=float(r.dua_res), cand_row_iters=float(r.cand_row_iters),
         rel_steps=[float(r.rel_step[i]) for i in range(n)],

@@ -88,6 +88,7 @@ typedef struct scp_b200_record {
   int64_t cycles_total, cycles_admm, cycles_polish; /* SM clock cycles spent on this scenario */
   int32_t polish_rounds;   /* add/drop rounds over all polish attempts */
   int32_t reserved2;
+  int64_t cycles_pbuild, cycles_psolve, cycles_peval, cycles_papply; /* polish breakdown */
   double rel_step[SCP_B200_MAX_SCP_ITER]; /* scp.py:157-160, one per trip */
 } scp_b200_record;
 
