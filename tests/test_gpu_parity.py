@@ -370,3 +370,47 @@ def test_c3_sized_kernels_properties(torch_cuda, lib):
     pb, vb = rec(a2, z, z)
     pc, vc = rec(a1 + 2 * a2, p0, z)
     assert np.abs(pc - (pa + 2 * pb)).max() <= 1e-9 and np.abs(vc - (va + 2 * vb)).max() <= 1e-10
+
+
+def test_c1_default_cli_problem_properties(torch_cuda, lib):
+    """BASELINE.json configs[0]: compute-trajectories defaults (10 agents, T=100 s, h=0.2 s -> K=500, 200 x 200 m).
+    The oracle needs a 10000 x 10000 dense factorisation per rho update for this size, so only properties are
+    checked: feasibility of the returned trajectory and agreement between the whole-grid and one-CTA kernels."""
+    from oracle import scp_oracle
+    from path_planning.scenarios.position_generator import generate_positions
+
+    random.seed(0)
+    p0, pf = generate_positions(10, 0.8)
+    space = [0, 0, 200, 200]
+    acc, pos, vel, recs = _solve_host(lib, p0, pf, 100, 0.2, 0.8, space)
+    r = recs[0]
+    assert pos.shape == (1, 10, 500, 2) and r["status"] == 0 and r["converged"]
+    z = np.zeros((10, 2))
+    assert scp_oracle.dynamics_residual(acc[0], p0, z, pf, z, 0.2, space, positions=pos[0]) <= DYN_TOL
+    assert r["min_separation"] >= 0.8 - 0.01
+    acc1, _, _, recs1 = _solve_host(lib, p0, pf, 100, 0.2, 0.8, space, team_mode=1)
+    assert recs1[0]["scp_iterations"] == r["scp_iterations"] and np.abs(acc1 - acc).max() <= 1e-9
+
+
+def test_batch_cli_records_and_files(torch_cuda, lib, tmp_path):
+    """compute-trajectories-batch (reference cli/compute_trajectories_batch.py:70-173): JSON/CSV schema and records."""
+    import csv
+    import json
+
+    from path_planning.cli import compute_trajectories_batch as ctb
+
+    cfg = dict(Ns=[5, 6], trials_per_N=3, results_dir=str(tmp_path), rng_seed=7)
+    res = ctb.main(cfg)
+    assert set(res) == {"meta", "runs", "summary"} and res["meta"]["schema_version"] == "1.0"
+    assert len(res["runs"]) == 6 and set(res["summary"]) == {"5", "6"}
+    for run in res["runs"]:
+        assert {"N", "status", "time_sec", "error", "K", "T", "h", "trial_index"} <= set(run)
+        assert run["status"] == "success" and run["K"] == 50 and run["time_sec"] > 0
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 2 and files[0].endswith(".csv") and files[1].endswith(".json")
+    rows = list(csv.DictReader(open(tmp_path / files[0])))
+    assert list(rows[0].keys()) == ["N", "trial_index", "status", "time_sec", "K", "T", "h", "error"] and len(rows) == 6
+    assert json.load(open(tmp_path / files[1]))["summary"]["5"]["count"] == 3
+    # the unbatched path (run_single_trial, reference :28-67) gives the same record keys
+    single = ctb.run_single_trial(5, {**ctb.CONFIG, **cfg}, rng=np.random)
+    assert {"N", "status", "time_sec", "error", "K", "T", "h"} <= set(single) and single["status"] == "success"
