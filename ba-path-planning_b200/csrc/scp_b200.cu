@@ -39,6 +39,8 @@ int fail(int code, const std::string& msg) {
 
 constexpr int SOLVE_THREADS = 512;
 constexpr size_t SMEM_BASE = (4 * scp::RED + scp::SH_EXTRA) * sizeof(double);   // scp::sh_doubles(RED)
+constexpr int QUEUE_CAP = 1 << 20;                        // quanta that can be re-queued per launch
+constexpr size_t HEADER_BYTES = 256 + (size_t)QUEUE_CAP * sizeof(int);
 constexpr size_t TEAM_SCRATCH_BYTES = (size_t)24 << 20;   // team-wide reduction columns for the cooperative kernel
 constexpr size_t SMEM_NMAT_LIMIT = 96 * 1024;
 constexpr size_t SMEM_TOTAL_LIMIT = 227 * 1024;
@@ -82,9 +84,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
                  const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
                  double* ws_d, int* ws_i, double* acc, double* pos, double* vel, scp_b200_record* rec,
-                 unsigned int* counter, int nmat_in_smem, int hot_mask) {
+                 unsigned int* counter, int* queue, int resumable, int nmat_in_smem, int hot_mask) {
   extern __shared__ double smem[];
-  __shared__ int s_b;
+  __shared__ int s_b, s_fresh;
   scp::Ctx c;
   c.nthreads = blockDim.x;
   c.team = 1; c.tid0 = 0; c.np = blockDim.x < 512 ? blockDim.x : 512; c.rs = scp::RED; c.sh = smem;
@@ -110,19 +112,45 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     c.a_P = ptr[0]; c.a_F = ptr[1]; c.a_x = ptr[2]; c.a_vp = ptr[3]; c.a_vv = ptr[4]; c.a_vj = ptr[5]; c.a_va = ptr[6]; c.a_rhs = ptr[7];
     c.fused_epl = fused_ok ? 2 : 0;
   }
+  // Work queue of quanta (one SCP iteration each).  Items 0..B-1 are the scenarios themselves; a scenario that is not
+  // finished after its quantum is pushed to the tail, so long scenarios interleave with short ones and the batch
+  // ends within one quantum of the balanced finish time instead of one whole scenario.
+  // header: counter[0] = head, counter[1] = pushes, counter[2] = finished scenarios; queue[] starts at -1.
   for (;;) {
-    if (threadIdx.x == 0) s_b = (int)atomicAdd(counter, 1u);
+    if (threadIdx.x == 0) {
+      int b = -1;
+      const unsigned h = atomicAdd(&counter[0], 1u);
+      s_fresh = h < (unsigned)B;
+      if (h < (unsigned)B) b = (int)h;
+      else if (resumable && h - (unsigned)B < (unsigned)QUEUE_CAP) {
+        volatile int* slot = queue + (h - (unsigned)B);
+        volatile unsigned* fin = counter + 2;
+        for (;;) {
+          const int v = *slot;
+          if (v >= 0) { b = v; break; }
+          if (*fin >= (unsigned)B) break;
+          __nanosleep(500);
+        }
+      }
+      s_b = b;
+    }
     __syncthreads();
-    const int b = s_b;
+    const int b = s_b, fresh = s_fresh;
     __syncthreads();
-    if (b >= B) break;
+    if (b < 0) break;
+    __threadfence();                                   // another SM may have written this scenario's record / iterate
     const size_t s2 = (size_t)b * c.N * 2, s3 = (size_t)b * c.N * c.K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
-    scp::solve_scenario(c);
+    const int done = scp::solve_scenario(c, resumable ? (fresh ? 2 : 1) : 0);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (done) atomicAdd(&counter[2], 1u);
+      else { const unsigned t = atomicAdd(&counter[1], 1u); if (t < (unsigned)QUEUE_CAP) atomicExch(queue + t, b); }
+    }
   }
 }
-
 
 // ---------------------------------------------------------------------------------- team kernel
 // One large scenario at a time solved by the WHOLE cooperative grid (one CTA per SM): the same phase
@@ -149,7 +177,7 @@ scp_solve_team_kernel(const __grid_constant__ scp::Params g, int B, const double
     const size_t s2 = (size_t)b * c.N * 2, s3 = (size_t)b * c.N * c.K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
-    scp::solve_scenario(c);
+    scp::solve_scenario(c, 0);
     scp_team_sync(c.team);
   }
 }
@@ -323,7 +351,7 @@ int scp_b200_build_tables(const scp_b200_problem* prob, void* d_tables, void* st
 
 size_t scp_b200_workspace_bytes(const scp_b200_problem* prob, int slots) {
   scp::Layout L = scp::make_layout(prob->n_agents, prob->n_steps);
-  return slot_bytes(L) * (size_t)slots + 256 + TEAM_SCRATCH_BYTES;
+  return slot_bytes(L) * (size_t)slots + HEADER_BYTES + TEAM_SCRATCH_BYTES;
 }
 
 int scp_b200_default_slots(const scp_b200_problem* prob) {
@@ -354,14 +382,17 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   const double* tb = (const double*)d_tables;
   g.tb.B1 = tb; g.tb.B2 = tb + (size_t)K * K; g.tb.rj = tb + 2 * (size_t)K * K;
   g.tb.ra = g.tb.rj + K; g.tb.rv = g.tb.ra + K; g.tb.rp = g.tb.rv + K; g.tb.rc = g.tb.rp + K;
-  const size_t need = slot_bytes(g.L) * (size_t)slots + 256 + TEAM_SCRATCH_BYTES;
+  const size_t need = slot_bytes(g.L) * (size_t)slots + HEADER_BYTES + TEAM_SCRATCH_BYTES;
   if (workspace_bytes < need) return fail(2, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)d_workspace;
   unsigned int* counter = (unsigned int*)base;
-  double* ws_d = (double*)(base + 256);
-  int* ws_i = (int*)(base + 256 + g.L.n_double * sizeof(double) * (size_t)slots);
+  int* queue = (int*)(base + 256);
+  double* ws_d = (double*)(base + HEADER_BYTES);
+  int* ws_i = (int*)(base + HEADER_BYTES + g.L.n_double * sizeof(double) * (size_t)slots);
   CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
+  const int resumable = ((long long)B * (prob->max_scp_iter + 2) <= (long long)QUEUE_CAP) ? 1 : 0;
+  if (resumable) CUDA_OK(cudaMemsetAsync(queue, 0xFF, (size_t)B * (prob->max_scp_iter + 2) * sizeof(int), st));
   int hot_mask = 0;
   const size_t nm = nmat_smem_bytes(K);
   const size_t smem = plan_smem(prob->n_agents, K, &hot_mask);
@@ -373,7 +404,7 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   const bool team_mode = coop && prob->team_mode != 1 && (prob->team_mode == 2 || (B <= 8 && (size_t)2 * prob->n_agents * K >= 8192));
   if (team_mode) {
-    double* team_scratch = (double*)(base + 256 + slot_bytes(g.L) * (size_t)slots);
+    double* team_scratch = (double*)(base + HEADER_BYTES + slot_bytes(g.L) * (size_t)slots);
     if (scp::sh_doubles((size_t)sms * SOLVE_THREADS) * sizeof(double) > TEAM_SCRATCH_BYTES) return fail(3, "team scratch too small");
     void* args[] = {(void*)&g, (void*)&B, (void*)&d_p0, (void*)&d_v0, (void*)&d_pf, (void*)&d_vf, (void*)&ws_d, (void*)&ws_i,
                     (void*)&team_scratch, (void*)&d_acc, (void*)&d_pos, (void*)&d_vel, (void*)&d_records};
@@ -381,7 +412,7 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   } else {
     const int grid = B < slots ? B : slots;
     scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
-                                                          d_vel, d_records, counter, nm ? 1 : 0, hot_mask);
+                                                          d_vel, d_records, counter, queue, resumable, nm ? 1 : 0, hot_mask);
   }
   CUDA_OK(cudaGetLastError());
   return 0;

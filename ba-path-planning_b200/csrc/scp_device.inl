@@ -1792,44 +1792,66 @@ SCP_DEV void write_outputs(Ctx& c) {
 }
 
 // ------------------------------------------------------------------ the SCP loop
-SCP_DEV void solve_scenario(Ctx& c) {
+// resumable = 0: the whole loop scp.py:131-180 in one call.
+// resumable = 1 (later quanta) / 2 (first quantum): one quantum -- the initial QP + gate + first SCP iteration on the first call, one SCP iteration on
+// every later call; between quanta the scenario lives in its record (stage in `reserved2`) and in its `acc` output.
+// A suspended subproblem restarts from its accelerations only, which is all the reference carries between
+// iterations too (scp.py:155-166).  Returns 1 when the scenario is finished.
+SCP_DEV int solve_scenario(Ctx& c, int resumable) {
   const int K = c.K, N = c.N;
   double* red = c.sh;
   scp_b200_record r;
-  r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
-  r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
-  r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.polish_rounds = 0; r.reserved2 = 0;
-  r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0;
- 
-  r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
-  r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
-  r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
-  r.cand_row_iters = 0;
-  for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
+  int stage = 0;
+  if (resumable == 1) { r = *c.rec; stage = r.reserved2; }    // resumable == 2: first quantum, the record is not initialised yet
+  if (stage != 1) {
+    stage = 0;
+    r.status = SCP_B200_STATUS_OK; r.scp_iterations = 0; r.converged = 0; r.initial_feasible = 0;
+    r.admm_iterations = 0; r.qp_unsolved = 0; r.qp_infeasible = 0; r.polish_attempts = 0;
+    r.cycles_total = r.cycles_admm = r.cycles_polish = 0; r.polish_rounds = 0; r.reserved2 = 0;
+    r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
+    r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
+    r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
+    r.cand_row_iters = 0;
+    for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
+  }
 
   setup_scenario(c);
   c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0;
   c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
   const long long t_begin = SCP_CLOCK();
-  factor_operator(c);
-  AdmmOut a0 = solve_qp(c, 0, 0);
-  r.polish_ok += a0.certified; r.polish_attempts += a0.polish_attempts;                       // QP #0, scp.py:138
-  r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
-  if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
-  forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
   double minsep; long long frow; double fdist;
-  gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
-  int feasible = frow < 0;
-  r.initial_feasible = feasible;
-  if (!feasible) {
-    long long npairs = (long long)N * (N - 1) / 2;
-    int k = (int)(frow / npairs); long long p = frow - (long long)k * npairs;
-    int i = 0; while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
-    r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = i + 1 + (int)p;
-    r.first_violation_dist = fdist;
-    if (k == 0) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
+  int feasible = 0, it = 0, converged = 0;
+  if (stage == 0) {
+    factor_operator(c);
+    AdmmOut a0 = solve_qp(c, 0, 0);
+    r.polish_ok += a0.certified; r.polish_attempts += a0.polish_attempts;                       // QP #0, scp.py:138
+    r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
+    if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
+    forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
+    gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
+    feasible = frow < 0;
+    r.initial_feasible = feasible;
+    if (!feasible) {
+      long long npairs = (long long)N * (N - 1) / 2;
+      int k = (int)(frow / npairs); long long p = frow - (long long)k * npairs;
+      int i = 0; while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
+      r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = i + 1 + (int)p;
+      r.first_violation_dist = fdist;
+      if (k == 0) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
+    }
+  } else {
+    // resume: accelerations of the last iterate -> x, positions
+    double* xr = c.a_x;
+    SCP_PHASE(c) {
+      for (int e = tid; e < c.Q * K; e += c.nthreads) {
+        int q = e / K, k = e - q * K;
+        xr[e] = c.acc[((size_t)(q >> 1) * K + k) * 2 + (q & 1)];
+      }
+    }
+    SCP_SYNC(c);
+    forward_rows(c, 0);
+    it = r.scp_iterations;
   }
-  int it = 0, converged = 0;
   double* x = c.a_x;
   double* xprev = c.wd + c.g->L.xprev;
   double* P = c.a_P;
@@ -1875,8 +1897,25 @@ SCP_DEV void solve_scenario(Ctx& c) {
     if (it < SCP_B200_MAX_SCP_ITER) r.rel_step[it] = rel;
     if (rel <= c.g->pb.scp_tolerance) converged = 1;
     ++it;
+    if (resumable) break;
   }
   r.scp_iterations = it; r.converged = converged;
+  r.cycles_total += SCP_CLOCK() - t_begin; r.cycles_admm += c.t_admm; r.cycles_polish += c.t_polish; r.polish_rounds += c.polish_rounds;
+  r.cycles_pbuild += c.t_pbuild; r.cycles_psolve += c.t_psolve; r.cycles_peval += c.t_peval; r.cycles_papply += c.t_papply;
+  if (resumable && r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
+    // suspend: the iterate goes to the scenario's acc output, the counters to its record
+    r.reserved2 = 1;
+    SCP_PHASE(c) {
+      for (int e = tid; e < c.Q * K; e += c.nthreads) {
+        int q = e / K, k = e - q * K;
+        c.acc[((size_t)(q >> 1) * K + k) * 2 + (q & 1)] = x[e];
+      }
+      if (tid == 0) *c.rec = r;
+    }
+    SCP_SYNC(c);
+    return 0;
+  }
+  r.reserved2 = 2;
   forward_rows(c, 0);
   gate_and_minsep(c, &minsep, &frow, &fdist);
   r.min_separation = minsep;
@@ -1888,10 +1927,9 @@ SCP_DEV void solve_scenario(Ctx& c) {
   SCP_SYNC(c);
   r.objective = reduce_finish(c, 0, 1);
   write_outputs(c);
-  r.cycles_total = SCP_CLOCK() - t_begin; r.cycles_admm = c.t_admm; r.cycles_polish = c.t_polish; r.polish_rounds = c.polish_rounds;
-  r.cycles_pbuild = c.t_pbuild; r.cycles_psolve = c.t_psolve; r.cycles_peval = c.t_peval; r.cycles_papply = c.t_papply;
   SCP_PHASE(c) { if (tid == 0) *c.rec = r; }
   SCP_SYNC(c);
+  return 1;
 }
 
 }  // namespace scp

@@ -14,6 +14,7 @@
 extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const double* p0, const double* v0,
                                    const double* pf, const double* vf, double* acc, double* pos,
                                    double* vel, scp_b200_record* rec, int nthreads) {
+  const int resumable = std::getenv("SCP_EMU_WHOLE") ? 0 : 1;
   using namespace scp;
   const int N = prob->n_agents, K = prob->n_steps;
   HostTables ht = build_host_tables(*prob);
@@ -37,7 +38,8 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
     size_t s2 = (size_t)b * N * 2, s3 = (size_t)b * N * K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
-    solve_scenario(c);
+    int mode = resumable ? 2 : 0;
+    while (!solve_scenario(c, mode)) mode = 1;   // quanta until the scenario is finished
   }
   return 0;
 }
