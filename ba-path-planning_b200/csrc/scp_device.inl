@@ -163,7 +163,7 @@ struct Ctx {
   int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
   double* fused_rows;           // per-warp right-hand-side rows (shared)
   int polish_rounds;            // add/drop rounds over all attempts of this scenario
-  int pol_valid, pol_n, pol_use_col;   // polish list/inverse state carried between attempts on one candidate set
+  int pol_valid, pol_n, pol_use_col, pol_col_stale;   // polish list/inverse state carried between attempts
   long long t_pbuild, t_psolve, t_peval, t_papply;
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   // block-uniform solver state
@@ -784,7 +784,7 @@ SCP_DEV void build_candidates(Ctx& c) {
   for (int e = 0; e < np; ++e) mx = pmax[e] > mx ? pmax[e] : mx;
   c.copies = mx;
   c.ncand = coff[total];
-  c.pol_valid = 0;                 // the candidate set changed: the polish list refers to the old CSR
+  c.pol_col_stale = 1;             // the candidate set changed: collision rows of the polish list refer to the old CSR
   SCP_SYNC(c);
   SCP_PHASE(c) {
     for (int t = tid; t < total; t += c.nthreads) {
@@ -1179,23 +1179,35 @@ SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_
   return n;
 }
 
-// y = Ainv rhs with two refinement sweeps on G0
-SCP_DEV void polish_solve(Ctx& c, int n) {
+// y = Ainv rhs, refined against the exact G0 until the residual is at rounding level.  The incrementally updated
+// inverse drifts (and is ruined by a nearly dependent row), so the residual is the health check of the list:
+// returns 0 when it cannot be brought down, and the caller rebuilds the list from scratch on its next attempt.
+SCP_DEV int polish_solve(Ctx& c, int n) {
   const int ld = c.g->L.pcap;
   const double* A = c.wd + c.g->L.pL;
   const double* G0 = c.wd + c.g->L.pG;
   const double* rhs = c.wd + c.g->L.prhs;
   double* y = c.wd + c.g->L.py;
   double* z = c.wd + c.g->L.scr;
-  for (int sweep = 0; sweep < 2; ++sweep) {
+  double* red = c.sh;
+  double bnorm = 0.0;
+  for (int sweep = 0; sweep < 6; ++sweep) {
     SCP_PHASE(c) {
+      double zm = 0.0, bm = 0.0;
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = rhs[r];
         if (sweep > 0) for (int q2 = 0; q2 < n; ++q2) acc -= G0[(size_t)q2 * ld + r] * y[q2];
         z[r] = acc;
+        zm = SCP_FMAX(zm, fabs(acc)); bm = SCP_FMAX(bm, fabs(rhs[r]));
       }
+      red[tid] = zm; red[c.rs + tid] = bm;
     }
     SCP_SYNC(c);
+    const double znorm = reduce_finish(c, 0, 0);
+    if (sweep == 0) bnorm = reduce_finish(c, 1, 0);
+    if (!(znorm == znorm)) return 0;
+    if (sweep > 0 && znorm <= 1e-12 * (1.0 + bnorm)) return 1;
+    if (sweep == 5) return znorm <= 1e-9 * (1.0 + bnorm);
     SCP_PHASE(c) {
       for (int r = tid; r < n; r += c.nthreads) {
         double acc = 0.0;
@@ -1205,6 +1217,7 @@ SCP_DEV void polish_solve(Ctx& c, int n) {
     }
     SCP_SYNC(c);
   }
+  return 1;
 }
 
 // One full polish.  Returns 1 when the active set is stable (KKT certificate on the carried
@@ -1242,8 +1255,18 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
 
   // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0.  The list, its inverse and the
   // marks survive between attempts on the same candidate set, so only the difference to the new guess is applied.
-  const int fresh = !(c.pol_valid && c.pol_use_col == use_col);
+  // The box rows of the list do not depend on the linearisation (their Gram entries are functions of type and step
+  // only), so they survive a new candidate set / a new subproblem; collision rows are dropped and re-entered.
+  const int fresh = !c.pol_valid;
+  const int col_fresh = fresh || c.pol_col_stale || c.pol_use_col != use_col;
   long long tq = SCP_CLOCK();
+  if (!fresh && col_fresh) {
+    int n0 = c.pol_n;
+    const int* ptype = c.wi + c.g->L.ptype;
+    for (int p = n0 - 1; p >= 0; --p)
+      if (ptype[p] == 4) n0 = polish_drop(c, p, n0);
+    c.pol_n = n0;
+  }
   SCP_PHASE(c) {
     for (int e = tid; e < QK; e += c.nthreads) {
       int q = e / K, k = e - q * K;
@@ -1269,7 +1292,7 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
         for (int sidx = coff[k * N + i]; sidx < coff[k * N + i + 1]; ++sidx) {
           pcscore[sidx] = 1.0;
           pcdec[sidx] = lam[((size_t)k * N + i) * N + cj[sidx]] > 0.0;
-          if (fresh) {
+          if (col_fresh) {
             pcmark[sidx] = 0; pcpos[sidx] = -1;
             pcown[sidx] = cj[sidx] > i ? k * N + i : -1;     // the i<j entry is the row's identity
           }
@@ -1279,13 +1302,13 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   SCP_SYNC(c);
   int n = polish_apply(c, g, fresh ? 0 : c.pol_n, use_col, 0.0, 0.0);
   c.t_pbuild += SCP_CLOCK() - tq;
-  c.pol_use_col = use_col; c.pol_n = n; c.pol_valid = n >= 0;
+  c.pol_use_col = use_col; c.pol_n = n; c.pol_valid = n >= 0; c.pol_col_stale = 0;
   if (n < 0) return 0;
 
   for (int round = 0; round < max_rounds; ++round) {
     c.polish_rounds++;
     tq = SCP_CLOCK();
-    if (n > 0) polish_solve(c, n);
+    if (n > 0 && !polish_solve(c, n)) { c.pol_valid = 0; return 0; }
     c.t_psolve += SCP_CLOCK() - tq;
     tq = SCP_CLOCK();
     // scatter multipliers to the dense arrays
@@ -1816,7 +1839,7 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
   }
 
   setup_scenario(c);
-  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0;
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0; c.pol_col_stale = 0;
   c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
   const long long t_begin = SCP_CLOCK();
   double minsep; long long frow; double fdist;
