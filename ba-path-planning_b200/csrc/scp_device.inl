@@ -1206,7 +1206,7 @@ SCP_DEV int polish_solve(Ctx& c, int n) {
     const double znorm = reduce_finish(c, 0, 0);
     if (sweep == 0) bnorm = reduce_finish(c, 1, 0);
     if (!(znorm == znorm)) return 0;
-    if (sweep > 0 && znorm <= 1e-12 * (1.0 + bnorm)) return 1;
+    if (sweep > 0 && znorm <= 1e-11 * (1.0 + bnorm)) return 1;
     if (sweep == 5) return znorm <= 1e-9 * (1.0 + bnorm);
     SCP_PHASE(c) {
       for (int r = tid; r < n; r += c.nthreads) {
@@ -1255,18 +1255,9 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
 
   // initial guess of W from the ADMM state: y != 0  <=>  v outside its box; lam > 0.  The list, its inverse and the
   // marks survive between attempts on the same candidate set, so only the difference to the new guess is applied.
-  // The box rows of the list do not depend on the linearisation (their Gram entries are functions of type and step
-  // only), so they survive a new candidate set / a new subproblem; collision rows are dropped and re-entered.
-  const int fresh = !c.pol_valid;
-  const int col_fresh = fresh || c.pol_col_stale || c.pol_use_col != use_col;
+  const int fresh = !(c.pol_valid && c.pol_use_col == use_col && !c.pol_col_stale);
+  const int col_fresh = fresh;
   long long tq = SCP_CLOCK();
-  if (!fresh && col_fresh) {
-    int n0 = c.pol_n;
-    const int* ptype = c.wi + c.g->L.ptype;
-    for (int p = n0 - 1; p >= 0; --p)
-      if (ptype[p] == 4) n0 = polish_drop(c, p, n0);
-    c.pol_n = n0;
-  }
   SCP_PHASE(c) {
     for (int e = tid; e < QK; e += c.nthreads) {
       int q = e / K, k = e - q * K;
