@@ -264,26 +264,33 @@ scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int 
   const long long pa = (long long)chunk * per, pb = min(P, pa + per);
   double mn = INFINITY;
   unsigned long long fr = ~0ull;
+  // each thread walks its pair indices p = pa + tid, pa + tid + T, ...; (i, j) is advanced incrementally
+  int i0 = 0, j0 = 0;
+  const long long pfirst = pa + threadIdx.x;
+  if (pfirst < pb) pair_from_index(pfirst, N, i0, j0);
+  const int T = blockDim.x;
   for (int kk = 0; kk < kn; ++kk) {
     const int k = k0 + kk;
     const double2* row = sp + kk * N;
     const size_t obase = ((size_t)b * K + k) * (size_t)P;
-    for (long long p = pa + threadIdx.x; p < pb; p += blockDim.x) {
-      int i, j;
-      pair_from_index(p, N, i, j);
+    int i = i0, j = j0;
+    for (long long p = pfirst; p < pb; p += T) {
       const double2 a = row[i], c = row[j];
       const double dx = a.x - c.x, dy = a.y - c.y;
-      double dist = hypot(dx, dy);                      // np.hypot, scp.py:501
-      const double dchk = sqrt(dx * dx + dy * dy);      // np.linalg.norm, scp.py:609
-      mn = fmin(mn, dchk);
-      if (dchk < thr) { unsigned long long r = (unsigned long long)k * (unsigned long long)P + (unsigned long long)p; fr = r < fr ? r : fr; }
+      // one square root serves both np.hypot (scp.py:501) and np.linalg.norm (scp.py:609): same value to 1 ulp
+      double dist = sqrt(dx * dx + dy * dy);
+      mn = fmin(mn, dist);
+      if (dist < thr) { unsigned long long r = (unsigned long long)k * (unsigned long long)P + (unsigned long long)p; fr = r < fr ? r : fr; }
       if (eta) {
         double ex, ey;
         if (dist < 1e-6) { ex = 1.0; ey = 0.0; dist = 1.0; }   // deterministic stand-in for scp.py:503-507
-        else { ex = dx / dist; ey = dy / dist; }
+        else { const double inv = 1.0 / dist; ex = dx * inv; ey = dy * inv; }
         eta[obase + p] = make_double2(ex, ey);
         bound[obase + p] = R + ((ex * dx + ey * dy) - dist);   // scp.py:547-549 without the p0/v0 shift (T3)
       }
+      // advance (i, j) by T pairs in lexicographic i<j order
+      j += T;
+      while (j >= N) { const int over = j - N; ++i; j = i + 1 + over; if (i >= N - 1) break; }
     }
   }
   // warp shuffle reduction, then one atomic per warp (positive doubles order like their bit patterns)
@@ -310,7 +317,7 @@ __global__ void scp_linearize_finish_kernel(const unsigned long long* minsep_bit
                                             int B, int N, double* minsep, int32_t* first) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  if (minsep) minsep[b] = __longlong_as_double((long long)minsep_bits[b]);
+  if (minsep) minsep[b] = (minsep_bits[b] == ~0ull) ? INFINITY : __longlong_as_double((long long)minsep_bits[b]);
   if (first) {
     const unsigned long long P = (unsigned long long)N * (N - 1) / 2;
     if (first_row[b] == ~0ull || P == 0) { first[3 * b] = first[3 * b + 1] = first[3 * b + 2] = -1; }
@@ -501,7 +508,7 @@ int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, doubl
   // scratch for the two 64-bit reductions, allocated stream-ordered
   unsigned long long* red = nullptr;
   CUDA_OK(cudaMallocAsync((void**)&red, 2 * (size_t)B * sizeof(unsigned long long), st));
-  scp_linearize_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(red, red + B, B);
+  CUDA_OK(cudaMemsetAsync(red, 0xFF, 2 * (size_t)B * sizeof(unsigned long long), st));   // +inf / no row, as ordered bit patterns
   if (N >= 2) {
     int KT = 8;
     while (KT > 1 && (size_t)KT * N * sizeof(double2) > 200 * 1024) KT >>= 1;
@@ -509,7 +516,7 @@ int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, doubl
     const int ktiles = (K + KT - 1) / KT;
     const long long P = (long long)N * (N - 1) / 2;
     long long want = (4LL * 148 + (long long)B * ktiles - 1) / ((long long)B * ktiles);   // >= 4 CTAs per SM in total
-    long long maxc = (P + 2047) / 2048;
+    long long maxc = (P + 511) / 512;
     int nchunks = (int)(want < 1 ? 1 : (want > maxc ? maxc : want));
     if (nchunks < 1) nchunks = 1;
     const size_t smem = (size_t)KT * N * sizeof(double2);
