@@ -506,16 +506,27 @@ int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, doubl
   if ((d_eta == nullptr) != (d_bound == nullptr)) return fail(1, "d_eta and d_bound must both be given or both NULL");
   cudaStream_t st = (cudaStream_t)stream;
   // scratch for the two 64-bit reductions, allocated stream-ordered
+  {  // keep the stream-ordered pool's memory between calls (the default threshold returns it at every sync)
+    static std::once_flag once;
+    std::call_once(once, [] {
+      int dev = 0; cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    });
+  }
   unsigned long long* red = nullptr;
   CUDA_OK(cudaMallocAsync((void**)&red, 2 * (size_t)B * sizeof(unsigned long long), st));
   CUDA_OK(cudaMemsetAsync(red, 0xFF, 2 * (size_t)B * sizeof(unsigned long long), st));   // +inf / no row, as ordered bit patterns
   if (N >= 2) {
+    // position tile of KT steps in shared memory; kept <= 32 KB so that 6-7 CTAs share an SM (streaming kernel)
     int KT = 8;
-    while (KT > 1 && (size_t)KT * N * sizeof(double2) > 200 * 1024) KT >>= 1;
+    while (KT > 1 && (size_t)KT * N * sizeof(double2) > 32 * 1024) KT >>= 1;
     if ((size_t)KT * N * sizeof(double2) > 200 * 1024) { cudaFreeAsync(red, st); return fail(1, "n_agents too large for the position tile"); }
     const int ktiles = (K + KT - 1) / KT;
     const long long P = (long long)N * (N - 1) / 2;
-    long long want = (4LL * 148 + (long long)B * ktiles - 1) / ((long long)B * ktiles);   // >= 4 CTAs per SM in total
+    long long want = (8LL * 148 + (long long)B * ktiles - 1) / ((long long)B * ktiles);   // >= 8 CTAs per SM in total
     long long maxc = (P + 511) / 512;
     int nchunks = (int)(want < 1 ? 1 : (want > maxc ? maxc : want));
     if (nchunks < 1) nchunks = 1;
