@@ -247,7 +247,8 @@ __device__ __forceinline__ void pair_from_index(long long p, int N, int& i, int&
 }
 
 __global__ void __launch_bounds__(LIN_THREADS)
-scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int nchunks, double R, double thr,
+scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int nchunks, long long p_begin, long long p_end,
+                     double R, double thr,
                      double2* __restrict__ eta, double* __restrict__ bound,
                      unsigned long long* __restrict__ minsep_bits, unsigned long long* __restrict__ first_row) {
   extern __shared__ double2 sp[];                       // [KT][N]
@@ -260,8 +261,9 @@ scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int 
     sp[kk * N + i] = src[(size_t)i * K + k0 + kk];
   }
   __syncthreads();
-  const long long per = (P + nchunks - 1) / nchunks;
-  const long long pa = (long long)chunk * per, pb = min(P, pa + per);
+  const long long Pr = p_end - p_begin;               // rows of this call (a rank's share of the pair indices)
+  const long long per = (Pr + nchunks - 1) / nchunks;
+  const long long pa = p_begin + (long long)chunk * per, pb = min(p_end, pa + per);
   double mn = INFINITY;
   unsigned long long fr = ~0ull;
   // each thread walks its pair indices p = pa + tid, pa + tid + T, ...; (i, j) is advanced incrementally
@@ -272,7 +274,7 @@ scp_linearize_kernel(const double2* __restrict__ pos, int N, int K, int KT, int 
   for (int kk = 0; kk < kn; ++kk) {
     const int k = k0 + kk;
     const double2* row = sp + kk * N;
-    const size_t obase = ((size_t)b * K + k) * (size_t)P;
+    const size_t obase = ((size_t)b * K + k) * (size_t)Pr - (size_t)p_begin;   // output row index is p - p_begin
     int i = i0, j = j0;
     for (long long p = pfirst; p < pb; p += T) {
       const double2 a = row[i], c = row[j];
@@ -501,9 +503,17 @@ int scp_b200_reconstruct(const double* d_acc, const double* d_p0, const double* 
 
 int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, double feas_margin, double* d_eta,
                        double* d_bound, double* d_minsep, int32_t* d_first, void* stream) {
+  return scp_b200_linearize_range(d_pos, B, N, K, R, feas_margin, 0, (int64_t)N * (N - 1) / 2, d_eta, d_bound, d_minsep,
+                                  d_first, stream);
+}
+
+int scp_b200_linearize_range(const double* d_pos, int B, int N, int K, double R, double feas_margin, int64_t pair_begin,
+                             int64_t pair_end, double* d_eta, double* d_bound, double* d_minsep, int32_t* d_first,
+                             void* stream) {
   if (B <= 0) return 0;
   if (N < 1 || K < 1) return fail(1, "bad sizes");
   if ((d_eta == nullptr) != (d_bound == nullptr)) return fail(1, "d_eta and d_bound must both be given or both NULL");
+  if (pair_begin < 0 || pair_end < pair_begin || pair_end > (int64_t)N * (N - 1) / 2) return fail(1, "bad pair range");
   cudaStream_t st = (cudaStream_t)stream;
   // scratch for the two 64-bit reductions, allocated stream-ordered
   {  // keep the stream-ordered pool's memory between calls (the default threshold returns it at every sync)
@@ -519,13 +529,13 @@ int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, doubl
   unsigned long long* red = nullptr;
   CUDA_OK(cudaMallocAsync((void**)&red, 2 * (size_t)B * sizeof(unsigned long long), st));
   CUDA_OK(cudaMemsetAsync(red, 0xFF, 2 * (size_t)B * sizeof(unsigned long long), st));   // +inf / no row, as ordered bit patterns
-  if (N >= 2) {
+  if (N >= 2 && pair_end > pair_begin) {
     // position tile of KT steps in shared memory; kept <= 32 KB so that 6-7 CTAs share an SM (streaming kernel)
     int KT = 8;
     while (KT > 1 && (size_t)KT * N * sizeof(double2) > 32 * 1024) KT >>= 1;
     if ((size_t)KT * N * sizeof(double2) > 200 * 1024) { cudaFreeAsync(red, st); return fail(1, "n_agents too large for the position tile"); }
     const int ktiles = (K + KT - 1) / KT;
-    const long long P = (long long)N * (N - 1) / 2;
+    const long long P = pair_end - pair_begin;
     long long want = (8LL * 148 + (long long)B * ktiles - 1) / ((long long)B * ktiles);   // >= 8 CTAs per SM in total
     long long maxc = (P + 511) / 512;
     int nchunks = (int)(want < 1 ? 1 : (want > maxc ? maxc : want));
@@ -533,7 +543,8 @@ int scp_b200_linearize(const double* d_pos, int B, int N, int K, double R, doubl
     const size_t smem = (size_t)KT * N * sizeof(double2);
     CUDA_OK(cudaFuncSetAttribute(scp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nchunks, ktiles, B);
-    scp_linearize_kernel<<<grid, LIN_THREADS, smem, st>>>((const double2*)d_pos, N, K, KT, nchunks, R,
+    scp_linearize_kernel<<<grid, LIN_THREADS, smem, st>>>((const double2*)d_pos, N, K, KT, nchunks, (long long)pair_begin,
+                                                          (long long)pair_end, R,
                                                           R - feas_margin, (double2*)d_eta, d_bound, red, red + B);
   }
   scp_linearize_finish_kernel<<<(B + 255) / 256, 256, 0, st>>>(red, red + B, B, N, d_minsep, d_first);

@@ -119,6 +119,11 @@ _SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
          C.c_void_p],
     ),
+    "scp_b200_linearize_range": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "scp_b200_linearize": (
         C.c_int,
         [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,

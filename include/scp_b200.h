@@ -157,6 +157,13 @@ int scp_b200_linearize(const double* d_pos, int n_scenarios, int n_agents, int n
                        double min_distance, double feas_margin, double* d_eta, double* d_bound,
                        double* d_minsep, int32_t* d_first, void* stream);
 
+/* Same for the pair indices [pair_begin, pair_end) only (pair index p = i(2N-i-1)/2 + j-i-1, i<j): the share of one
+ * rank when the agents of a large scenario are sharded over GPUs.  d_eta : (B,K,Pr,2), d_bound : (B,K,Pr) with
+ * Pr = pair_end - pair_begin; d_minsep / d_first reduce over this range only (combine across ranks with MIN). */
+int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents, int n_steps,
+                             double min_distance, double feas_margin, int64_t pair_begin, int64_t pair_end,
+                             double* d_eta, double* d_bound, double* d_minsep, int32_t* d_first, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

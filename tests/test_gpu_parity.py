@@ -414,3 +414,40 @@ def test_batch_cli_records_and_files(torch_cuda, lib, tmp_path):
     # the unbatched path (run_single_trial, reference :28-67) gives the same record keys
     single = ctb.run_single_trial(5, {**ctb.CONFIG, **cfg}, rng=np.random)
     assert {"N", "status", "time_sec", "error", "K", "T", "h"} <= set(single) and single["status"] == "success"
+
+
+def test_linearize_range_shards_concatenate_to_full(torch_cuda, lib):
+    """Agent-sharded linearisation (config 4's pairwise step): the per-rank pair ranges of scp_b200_linearize_range,
+    run one after the other on one GPU, reproduce the full kernel's rows bit for bit and its reductions via MIN."""
+    from path_planning import _capi
+    from path_planning.solvers.sharded import agent_blocks, pair_index
+
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    N, K, R = 300, 40, 0.8
+    pos = rng.uniform(0, 60, (1, N, K, 2))
+    eta_full, bound_full, minsep_full, first_full = _linearize(torch, lib, pos, R)
+    P = N * (N - 1) // 2
+    d_pos = _dev(torch, pos)
+    for world in (2, 8):
+        b = agent_blocks(N, world)
+        etas, bounds, mins, firsts = [], [], [], []
+        for g in range(world):
+            pb = pair_index(b[g], N)
+            pe = pair_index(b[g + 1], N) if b[g + 1] < N else P
+            rows = pe - pb
+            eta = torch.full((K, max(rows, 1), 2), float("nan"), dtype=torch.float64, device="cuda")
+            bound = torch.full((K, max(rows, 1)), float("nan"), dtype=torch.float64, device="cuda")
+            ms = torch.zeros(1, dtype=torch.float64, device="cuda")
+            fi = torch.zeros(3, dtype=torch.int32, device="cuda")
+            _capi.check(lib.scp_b200_linearize_range(d_pos.data_ptr(), 1, N, K, R, 0.01, pb, pe, eta.data_ptr(),
+                                                     bound.data_ptr(), ms.data_ptr(), fi.data_ptr(), None))
+            torch.cuda.synchronize()
+            etas.append(eta.cpu().numpy()[:, :rows]); bounds.append(bound.cpu().numpy()[:, :rows])
+            mins.append(float(ms[0])); firsts.append(tuple(int(v) for v in fi.tolist()))
+        assert np.array_equal(np.concatenate(etas, axis=1), eta_full[0])
+        assert np.array_equal(np.concatenate(bounds, axis=1), bound_full[0])
+        assert min(mins) == minsep_full[0]
+        rows_idx = [k * P + pair_index(i, N) + (j - i - 1) for (k, i, j) in firsts if k >= 0]
+        exp = tuple(first_full[0])
+        assert (min(rows_idx) if rows_idx else None) == (exp[0] * P + pair_index(exp[1], N) + exp[2] - exp[1] - 1 if exp[0] >= 0 else None)

@@ -88,3 +88,23 @@ def test_scenario_sharding_world_size_2_gloo():
         assert [r[0] for r in recs] == list(range(7))
         assert [r[1] for r in recs] == [0, 0, 0, 0, 1, 1, 1]
         assert np.allclose([r[2] for r in recs], p0.sum(axis=(1, 2)))
+
+
+def test_agent_blocks_balance_pair_rows():
+    from path_planning.solvers.sharded import agent_blocks, pair_index
+
+    for n in (2, 25, 200, 1000):
+        total = n * (n - 1) // 2
+        for w in (1, 2, 4, 8):
+            b = agent_blocks(n, w)
+            assert b[0] == 0 and b[-1] == n and all(b[g] <= b[g + 1] for g in range(w))
+            ends = [pair_index(b[g], n) if b[g] < n else total for g in range(w + 1)]
+            rows = [ends[g + 1] - ends[g] for g in range(w)]
+            assert sum(rows) == total
+            if n >= 200:
+                assert max(rows) - min(rows) <= 2 * n          # balanced to within two agents' worth of rows
+    # pair_index is the reference's lexicographic i<j order (scp.py:495-496)
+    n = 7
+    order = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    for p, (i, j) in enumerate(order):
+        assert pair_index(i, n) + (j - i - 1) == p
