@@ -75,27 +75,33 @@ class ShardedLinearizer:
         return self.pos_all
 
     def linearize(self, positions_own):
-        """Returns (eta (K,rows,2), bound (K,rows), min separation, first violating (k,i,j) or None), all global."""
+        """Returns this rank's rows eta (K,rows,2), bound (K,rows) and a 2-element device tensor with the GLOBAL
+        minimum separation and first violating row index (decode() turns it into (k,i,j))."""
         torch, dist = self.torch, self.dist
         pos = self.gather_positions(positions_own)
         st = torch.cuda.current_stream().cuda_stream
         _capi.check(self.lib.scp_b200_linearize_range(
             pos.data_ptr(), 1, self.N, self.K, self.R, self.margin, self.p_begin, self.p_end, self.eta.data_ptr(),
             self.bound.data_ptr(), self.minsep.data_ptr(), self.first.data_ptr(), st))
+        # reductions stay on the device (no host sync inside an SCP iteration): row = k P + p(i, j), +inf when none
         P = self.N * (self.N - 1) // 2
-        k, i, j = (int(v) for v in self.first.tolist())
-        row = float(k * P + pair_index(i, self.N) + (j - i - 1)) if k >= 0 else float("inf")
+        f = self.first.to(torch.float64)
+        k, i, j = f[0], f[1], f[2]
+        row = k * P + (i * (2 * self.N - i - 1)) * 0.5 + (j - i - 1)          # exact in fp64 for N <= 2^20
         self.red[0] = self.minsep[0]
-        self.red[1] = row
+        self.red[1] = torch.where(k >= 0, row, torch.full_like(row, float("inf")))
         if self.world > 1:
             dist.all_reduce(self.red, op=dist.ReduceOp.MIN, group=self.group)
-        minsep, row = float(self.red[0]), float(self.red[1])
-        first = None
-        if np.isfinite(row):
-            r = int(row)
-            k, p = divmod(r, P)
-            i = 0
-            while pair_index(i + 1, self.N) <= p:
-                i += 1
-            first = (k, i, i + 1 + p - pair_index(i, self.N))
-        return self.eta, self.bound, minsep, first
+        return self.eta, self.bound, self.red
+
+    def decode(self, red):
+        """Host view of the reductions: (min separation, first violating (k, i, j) or None).  Synchronises."""
+        minsep, row = (float(v) for v in red.tolist())
+        if not np.isfinite(row):
+            return minsep, None
+        P = self.N * (self.N - 1) // 2
+        k, p = divmod(int(row), P)
+        i = 0
+        while pair_index(i + 1, self.N) <= p:
+            i += 1
+        return minsep, (k, i, i + 1 + p - pair_index(i, self.N))

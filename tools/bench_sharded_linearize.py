@@ -41,6 +41,6 @@ P = N * (N - 1) // 2
 if rank == 0:
     nbytes = 8 * (2 * N * K + 3 * P * K)
     print(json.dumps(dict(case="sharded linearize", N=N, K=K, n_gpus=world, ms_linearize_incl_allgather_and_minreduce=float(t[0]),
-                          ms_allgather=float(t[1]), rows=P * K, algorithmic_bytes=nbytes, min_separation=out[2],
+                          ms_allgather=float(t[1]), rows=P * K, algorithmic_bytes=nbytes, min_separation=sl.decode(out[2])[0], first_violation=sl.decode(out[2])[1],
                           agent_bounds=sl.bounds, aggregate_gbs=nbytes / float(t[0]) / 1e6)))
 if world > 1: dist.destroy_process_group()
