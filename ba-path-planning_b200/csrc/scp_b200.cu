@@ -79,6 +79,9 @@ int validate(const scp_b200_problem* p) {
 
 }  // namespace
 
+// error slot shared with the other translation units of the library (scp_stream.cu)
+int scp_b200_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
 // ---------------------------------------------------------------------------------- solver kernel
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,

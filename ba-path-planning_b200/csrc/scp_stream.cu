@@ -1,0 +1,1175 @@
+// scp_stream.cu -- streaming SCP solver (sm_100a): the loop of scp.py:131-180 as a sequence of
+// HBM/L2-streaming kernels over ALL scenarios and agents of a batch, with the per-scenario control
+// flow (ADMM termination, rho adaptation, candidate verification, SCP convergence) decided on the
+// device by small control kernels, so the host only replays a fixed launch sequence and polls one
+// counter.  It is the path for scenarios too large for one CTA's shared memory (config 3: 200 agents,
+// config 5: batches of 50-200 agents) and for ONE scenario whose agents are sharded over the GPUs of a
+// node (config 4): rank g owns a block of agents, every ADMM iteration ends with an NCCL all-gather of
+// the positions (N*K*2 doubles), the residual scalars are all-gathered at check iterations.
+//
+// Same QP splitting as scp_device.inl: box rows in the v = z + y/rho form,
+// terminal equalities exact in the x-update, collision rows as contact-force iterations on per-agent
+// copies, one K x K operator per scenario.  No polish here: subproblems end on the ADMM residual test.
+//
+// Reference code replaced (src/path_planning/solvers/scp.py):
+//   k_axis<.,0/1>   x-update + rows of A x           OSQP iteration inside problem.solve() :362,:445
+//   k_collide       collision rows                    rows of _add_collision_constraints   :453-557
+//   k_build         candidate rows + linearisation    _add_collision_constraints           :487-549
+//   k_scan          gate / min separation / verify    _fast_check_avoidance_constraints    :597-615
+//   k_control*      termination + SCP loop            generate_trajectories                :152-166
+//   k_output        result dict                       :168-175
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: every NCCL function is resolved with dlsym at run time
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/scp_b200.h"
+#include "scp_tables.h"
+
+extern int scp_b200_set_error(int code, const char* msg);   // scp_b200.cu
+
+namespace ss {
+
+constexpr int NRED = 16;
+enum { R_PRI = 0, R_NPRI, R_DUA, R_NDUA, R_PRICOL, R_DN, R_PN, R_OBJ, R_MINSEP, R_FIRST, R_BAD, R_MAXD, R_COPIES, R_NCAND, R_OVER, R_SPARE };
+enum { FL_SCAN = 1, FL_GATE = 2, FL_VERIFY = 4, FL_SNAPSHOT = 8, FL_BUILD = 16, FL_KEEP = 32, FL_RESCALE = 64, FL_RESET = 128,
+       FL_FACTOR = 256, FL_FINISH = 512 };
+constexpr int MAXC_MAX = 48;
+constexpr int AX_THREADS = 256;
+
+struct State {
+  int phase;        // 0: initial QP, 1: QP with collision rows, 2: finished
+  int flags;        // work requested from the predicated kernels of this macro step
+  int qp_it, scp_it, copies, attempt, have_state, qp_solved, stalled, it_mark;
+  double rho, est, margin, pri_mark, ncand;
+  double pri, dua, dn, pn, obj, minsep;
+};
+
+struct Dev {
+  scp_b200_problem pb;
+  int B, N, K, Q, Qs;          // Qs = row stride of one scenario in the per-agent-axis arrays (>= Q, padded for the all-gather)
+  int a_lo, a_hi;              // agents owned by this rank
+  int maxc, G, rank;
+  const double *rj, *ra, *rv, *rp, *rc, *B1, *B2;
+  double *x, *xprev, *va, *vj, *vv, *vp, *P, *Pbar, *F, *FY, *mu, *qsum;
+  double *Nmat, *N0, *Qm, *gg;
+  const double *p0, *v0, *pf, *vf;
+  int *cnt, *cj;
+  double *cex, *cey, *cb, *lam;
+  double *slab, *gath;
+  State* st;
+  scp_b200_record* rec;
+  double *acc, *pos, *vel;     // (B, Npad, K, 2)
+  int Npad;
+  int* done;
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+  atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_min_pos(double* addr, double v) {
+  atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ double warp_max_nan(double v) {   // NaN-propagating max of non-negative values (bit order)
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(0xffffffffu, b, d); b = o > b ? o : b; }
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+template <int EPL>
+__device__ __forceinline__ void suffix_sum(double (&v)[EPL], int lane) {
+  double carry = 0.0;
+#pragma unroll
+  for (int e = EPL - 1; e >= 0; --e) {
+    double s = v[e];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { double o = __shfl_down_sync(0xffffffffu, s, d); if (lane + d < 32) s += o; }
+    s += carry; v[e] = s;
+    carry = __shfl_sync(0xffffffffu, s, 0);
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void prefix_sum(double (&v)[EPL], int lane) {
+  double carry = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    double s = v[e];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { double o = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += o; }
+    s += carry; v[e] = s;
+    carry = __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+
+// ---------------------------------------------------------------------------------- init
+__global__ void k_init(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y, K = d.K;
+  const double h = d.pb.time_step;
+  const size_t base = (size_t)b * d.Qs * K;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.Qs * K; e += gridDim.x * blockDim.x) {
+    const int q = e / K, k = e - q * K;
+    double p = 0.0;
+    if (q < d.Q) { const double p0 = d.p0[(size_t)b * d.Q + q], v0 = d.v0[(size_t)b * d.Q + q]; p = p0 + h * (double)k * v0; }
+    d.x[base + e] = 0.0; d.xprev[base + e] = 0.0; d.va[base + e] = 0.0; d.vj[base + e] = 0.0; d.vv[base + e] = 0.0; d.vp[base + e] = 0.0;
+    d.P[base + e] = p; d.Pbar[base + e] = p; d.F[base + e] = 0.0; d.FY[base + e] = 0.0;
+  }
+  const int Nown = d.a_hi - d.a_lo;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Nown * K; t += gridDim.x * blockDim.x) d.cnt[(size_t)b * Nown * K + t] = 0;
+  if (blockIdx.x == 0) {
+    for (int t = threadIdx.x; t < 2 * d.Qs; t += blockDim.x) d.mu[(size_t)b * 2 * d.Qs + t] = 0.0;
+    for (int t = threadIdx.x; t < NRED; t += blockDim.x)
+      d.slab[(size_t)b * NRED + t] = (t == R_MINSEP || t == R_FIRST) ? INFINITY : 0.0;
+    if (threadIdx.x == 0) {
+      State s;
+      s.phase = 0; s.flags = FL_FACTOR; s.qp_it = 0; s.scp_it = 0; s.copies = 0; s.attempt = 0; s.have_state = 0; s.qp_solved = 0;
+      s.stalled = 0; s.it_mark = 0; s.rho = d.pb.rho0; s.est = 1.0; s.margin = d.pb.cand_margin; s.pri_mark = INFINITY; s.ncand = 0.0;
+      s.pri = s.dua = INFINITY; s.dn = s.pn = s.obj = 0.0; s.minsep = INFINITY;
+      d.st[b] = s;
+      scp_b200_record r;
+      memset(&r, 0, sizeof(r));
+      r.status = SCP_B200_STATUS_OK;
+      r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
+      r.min_separation = INFINITY;
+      d.rec[b] = r;
+      if (b == 0) *d.done = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- operator
+// One CTA per scenario that asked for it: M(rho, copies) inverted in shared memory by Gauss-Jordan (SPD, no
+// pivoting), then the equality-constrained solution operator (scp_device.inl factor_operator):
+//   x = Nmat r + N0 d,  mu = Qm r - G d.
+__global__ void __launch_bounds__(512) k_factor(const __grid_constant__ Dev d) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, K = d.K, tid = threadIdx.x, nt = blockDim.x;
+  const State& S = d.st[b];
+  if (!(S.flags & FL_FACTOR)) return;
+  double* M = sm;
+  double* colb = sm + (size_t)K * K;
+  double* rowb = colb + K;
+  double* mc = rowb + K;            // 2K
+  __shared__ double G3[3];
+  const double rho = S.rho, sig = d.pb.sigma, cp = (double)S.copies, h = d.pb.time_step;
+  for (int e = tid; e < K * K; e += nt) {
+    const int r = e / K, c = e - r * K;
+    M[e] = rho * (d.B1[e] + cp * d.B2[e]) + (r == c ? 2.0 + sig : 0.0);
+  }
+  __syncthreads();
+  for (int p = 0; p < K; ++p) {
+    for (int e = tid; e < K; e += nt) { colb[e] = M[e * K + p]; rowb[e] = M[p * K + e]; }
+    __syncthreads();
+    const double ip = 1.0 / colb[p];
+    for (int e = tid; e < K * K; e += nt) {
+      const int r = e / K, c = e - r * K;
+      double v;
+      if (r == p) v = (c == p) ? ip : rowb[c] * ip;
+      else if (c == p) v = -colb[r] * ip;
+      else v = M[e] - colb[r] * rowb[c] * ip;
+      M[e] = v;
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += nt) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int j = 0; j < K; ++j) { const double m = M[k * K + j]; a0 += m * h; a1 += m * (h * h * ((double)(K - 1 - j) + 0.5)); }
+    mc[2 * k] = a0; mc[2 * k + 1] = a1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double h00 = 0, h01 = 0, h11 = 0;
+    for (int k = 0; k < K; ++k) {
+      const double cv = h, cpk = h * h * ((double)(K - 1 - k) + 0.5);
+      h00 += cv * mc[2 * k]; h01 += cv * mc[2 * k + 1]; h11 += cpk * mc[2 * k + 1];
+    }
+    const double det = h00 * h11 - h01 * h01;
+    G3[0] = h11 / det; G3[1] = -h01 / det; G3[2] = h00 / det;
+    d.gg[(size_t)b * 4 + 0] = G3[0]; d.gg[(size_t)b * 4 + 1] = G3[1]; d.gg[(size_t)b * 4 + 2] = G3[2];
+  }
+  __syncthreads();
+  const double g00 = G3[0], g01 = G3[1], g11 = G3[2];
+  double* N0 = d.N0 + (size_t)b * 2 * K;
+  double* Qm = d.Qm + (size_t)b * 2 * K;
+  for (int k = tid; k < K; k += nt) {
+    const double n0 = mc[2 * k] * g00 + mc[2 * k + 1] * g01, n1 = mc[2 * k] * g01 + mc[2 * k + 1] * g11;
+    N0[2 * k] = n0; N0[2 * k + 1] = n1;
+    Qm[k] = n0; Qm[K + k] = n1;
+    colb[k] = n0; rowb[k] = n1;
+  }
+  __syncthreads();
+  double* out = d.Nmat + (size_t)b * K * K;
+  for (int e = tid; e < K * K; e += nt) {
+    const int r = e / K, c = e - r * K;
+    out[e] = M[e] - (mc[2 * r] * colb[c] + mc[2 * r + 1] * rowb[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------- agent-axis kernel
+// One warp per (scenario, agent-axis): lanes hold the steps k = lane + 32 e.  MODE 0: one ADMM iteration of the
+// box rows and the x-update (scp_device.inl admm_iter_fused, state streamed from HBM/L2 instead of shared memory);
+// MODE 1: the same plus the primal residual terms and the equality multipliers (check iteration);
+// MODE 2: v := A x (multipliers reset at the start of a subproblem: OSQP warm start with x only, scp.py:443).
+template <int EPL, int MODE>
+__global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev d, int qpc) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (MODE <= 1) { if (S.phase >= 2) return; } else { if (!(S.flags & FL_RESET)) return; }
+  const int K = d.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int q_hi = 2 * d.a_hi;
+  const int qa = 2 * d.a_lo + blockIdx.x * qpc, qb = min(qa + qpc, q_hi);
+  if (qa >= qb) return;
+  double* Nm = sm;
+  double* myrhs = sm + (MODE <= 1 ? (size_t)K * K : 0) + (size_t)warp * K;
+  if (MODE <= 1) {
+    const double* src = d.Nmat + (size_t)b * K * K;
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) Nm[e] = src[e];
+    __syncthreads();
+  }
+  const double h = d.pb.time_step, ih = 1.0 / h, rho = S.rho, sig = d.pb.sigma;
+  const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
+  const double cpr = (double)S.copies * rho;
+  const double* N0 = d.N0 + (size_t)b * 2 * K;
+  const double* Qm = d.Qm + (size_t)b * 2 * K;
+  double trj[EPL], tra[EPL], trv[EPL], trp[EPL], trc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int k = lane + 32 * e;
+    const bool in = k < K;
+    trj[e] = in ? rho * d.rj[k] : 0.0; tra[e] = in ? rho * d.ra[k] : 0.0;
+    trv[e] = in ? rho * d.rv[k] : 0.0; trp[e] = in ? rho * d.rp[k] : 0.0;
+    trc[e] = in ? cpr * d.rc[k] : 0.0;
+  }
+  double pr = 0.0, nr = 0.0;
+  for (int q = qa + warp; q < qb; q += nw) {
+    const size_t row = ((size_t)b * d.Qs + q) * K;
+    const size_t q2 = (size_t)b * d.Q + q;
+    const double v0q = d.v0[q2], p0q = d.p0[q2];
+    const double lv = -vl - v0q, uv = vl - v0q;
+    const double plo = d.pb.space[q & 1], phi = d.pb.space[2 + (q & 1)];
+    double *x = d.x + row, *vj = d.vj + row, *va = d.va + row, *vv = d.vv + row, *vp = d.vp + row, *P = d.P + row;
+    const double* F = d.F + row;
+    double xn[EPL], sj[EPL], sa[EPL], sv[EPL], sp[EPL], off[EPL];
+    if (MODE <= 1) {
+      double xo[EPL], wj[EPL], wv[EPL], wp[EPL], wa[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = lane + 32 * e;
+        xo[e] = 0; sj[e] = sa[e] = sv[e] = sp[e] = 0; wj[e] = wv[e] = wp[e] = wa[e] = 0; off[e] = 0;
+        if (k < K) {
+          xo[e] = x[k];
+          double v = va[k], z = clampd(v, -al, al);
+          sa[e] = v - z; wa[e] = tra[e] * (2 * z - v);
+          if (k < K - 1) {
+            v = vj[k]; z = clampd(v, -jl, jl); sj[e] = v - z; wj[e] = trj[e] * (2 * z - v);
+            v = vv[k]; z = clampd(v, lv, uv); sv[e] = v - z; wv[e] = trv[e] * (2 * z - v);
+            off[e] = p0q + h * (double)(k + 1) * v0q;
+            v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - z;
+            wp[e] = trp[e] * (2 * z - v) + trc[e] * (P[k + 1] - off[e]) + F[k + 1];
+          }
+        }
+      }
+      // transpose: D'wj + wa + V'wv + S'wp
+      double r1v[EPL], r1p[EPL], r2p[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { r1v[e] = wv[e]; r1p[e] = wp[e]; }
+      suffix_sum<EPL>(r1v, lane);
+      suffix_sum<EPL>(r1p, lane);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) r2p[e] = r1p[e];
+      suffix_sum<EPL>(r2p, lane);
+      double last = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = lane + 32 * e;
+        double prev = __shfl_up_sync(0xffffffffu, wj[e], 1);
+        if (lane == 0) prev = last;
+        last = __shfl_sync(0xffffffffu, wj[e], 31);
+        if (k < K) myrhs[k] = sig * xo[e] + (prev - wj[e]) * ih + wa[e] + h * r1v[e] + h * h * (r2p[e] - 0.5 * r1p[e]);
+      }
+      __syncwarp();
+      // x = Nmat rhs + N0 d   (Nmat symmetric: lane walks its columns, rhs broadcast from the warp's shared row)
+      const double d0 = d.vf[q2] - v0q, d1 = d.pf[q2] - (p0q + h * (double)K * v0q);
+      int kc[EPL];
+      double a0[EPL], a1[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { const int k = lane + 32 * e; kc[e] = k < K ? k : K - 1; a0[e] = 0.0; a1[e] = 0.0; }
+      int j = 0;
+      for (; j + 1 < K; j += 2) {
+        const double r0 = myrhs[j], r1 = myrhs[j + 1];
+        const double* n0 = Nm + (size_t)j * K;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { a0[e] += n0[kc[e]] * r0; a1[e] += n0[K + kc[e]] * r1; }
+      }
+      if (j < K) {
+        const double r0 = myrhs[j];
+        const double* n0 = Nm + (size_t)j * K;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) a0[e] += n0[kc[e]] * r0;
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = lane + 32 * e;
+        xn[e] = (k < K) ? N0[2 * k] * d0 + N0[2 * k + 1] * d1 + (a0[e] + a1[e]) : 0.0;
+      }
+      if (MODE == 1) {
+        // mu = Qm rhs - G d
+        double m0 = 0.0, m1 = 0.0;
+        for (int jj = lane; jj < K; jj += 32) { const double r = myrhs[jj]; m0 += Qm[jj] * r; m1 += Qm[K + jj] * r; }
+        m0 = warp_sum(m0); m1 = warp_sum(m1);
+        if (lane == 0) {
+          const double* gg = d.gg + (size_t)b * 4;
+          d.mu[((size_t)b * d.Qs + q) * 2] = m0 - (gg[0] * d0 + gg[1] * d1);
+          d.mu[((size_t)b * d.Qs + q) * 2 + 1] = m1 - (gg[1] * d0 + gg[2] * d1);
+        }
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = lane + 32 * e;
+        xn[e] = (k < K) ? x[k] : 0.0;
+        sj[e] = sa[e] = sv[e] = sp[e] = 0.0;
+        off[e] = (k < K - 1) ? p0q + h * (double)(k + 1) * v0q : 0.0;
+      }
+    }
+    // forward rows and v update
+    double c1[EPL], c2[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) c1[e] = xn[e];
+    prefix_sum<EPL>(c1, lane);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) c2[e] = c1[e];
+    prefix_sum<EPL>(c2, lane);
+    double first_next = 0.0;
+#pragma unroll
+    for (int e = EPL - 1; e >= 0; --e) {
+      const int k = lane + 32 * e;
+      double nxt = __shfl_down_sync(0xffffffffu, xn[e], 1);
+      if (lane == 31) nxt = first_next;
+      first_next = __shfl_sync(0xffffffffu, xn[e], 0);
+      if (k < K) {
+        if (MODE <= 1) x[k] = xn[e];
+        const double nva = xn[e] + sa[e];
+        va[k] = nva;
+        if (MODE == 1) { pr = fmax(pr, fabs(xn[e] - clampd(nva, -al, al))); nr = fmax(nr, fabs(xn[e])); }
+        if (k < K - 1) {
+          const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
+          const double aj = (nxt - xn[e]) * ih;
+          const double nvj = aj + sj[e], nvv = rv_ + sv[e], nvp = rp_ + sp[e];
+          vj[k] = nvj; vv[k] = nvv; vp[k] = nvp;
+          P[k + 1] = off[e] + rp_;
+          if (MODE == 1) {
+            pr = fmax(pr, fabs(aj - clampd(nvj, -jl, jl)));
+            pr = fmax(pr, fabs(rv_ - clampd(nvv, lv, uv)));
+            pr = fmax(pr, fabs(rp_ - clampd(nvp, plo - off[e], phi - off[e])));
+            nr = fmax(nr, fmax(fabs(aj), fmax(fabs(rv_), fabs(rp_))));
+          }
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    pr = warp_max_nan(fabs(pr)); nr = warp_max_nan(fabs(nr));
+    if (lane == 0) { atomic_max_pos(d.slab + (size_t)b * NRED + R_PRI, pr); atomic_max_pos(d.slab + (size_t)b * NRED + R_NPRI, nr); }
+  }
+}
+
+// ---------------------------------------------------------------------------------- dual residual
+// rhs <- 2x + A'y + C'mu per agent-axis (scp_device.inl transpose_rows mode 1) reduced to max|.|, plus the
+// per-agent-axis sums ||x - xprev||^2, ||xprev||^2 (scp.py:157-160) and ||x||^2.
+template <int EPL>
+__global__ void __launch_bounds__(AX_THREADS) k_dual(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (S.phase >= 2) return;
+  const int K = d.K, lane = threadIdx.x & 31;
+  const int q = 2 * d.a_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (q >= 2 * d.a_hi) return;
+  const double h = d.pb.time_step, ih = 1.0 / h, rho = S.rho;
+  const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
+  const size_t row = ((size_t)b * d.Qs + q) * K;
+  const size_t q2 = (size_t)b * d.Q + q;
+  const double v0q = d.v0[q2], p0q = d.p0[q2];
+  const double lv = -vl - v0q, uv = vl - v0q;
+  const double plo = d.pb.space[q & 1], phi = d.pb.space[2 + (q & 1)];
+  const double *x = d.x + row, *xp = d.xprev + row, *vj = d.vj + row, *va = d.va + row, *vv = d.vv + row, *vp = d.vp + row, *FY = d.FY + row;
+  double xo[EPL], wj[EPL], wa[EPL], r1v[EPL], r1p[EPL], r2p[EPL];
+  double dn = 0.0, pn = 0.0, ob = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int k = lane + 32 * e;
+    xo[e] = 0; wj[e] = wa[e] = r1v[e] = r1p[e] = 0;
+    if (k < K) {
+      xo[e] = x[k];
+      const double xq = xp[k];
+      dn += (xo[e] - xq) * (xo[e] - xq); pn += xq * xq; ob += xo[e] * xo[e];
+      double v = va[k], z = clampd(v, -al, al);
+      wa[e] = rho * d.ra[k] * (v - z);
+      if (k < K - 1) {
+        v = vj[k]; z = clampd(v, -jl, jl); wj[e] = rho * d.rj[k] * (v - z);
+        v = vv[k]; z = clampd(v, lv, uv); r1v[e] = rho * d.rv[k] * (v - z);
+        const double off = p0q + h * (double)(k + 1) * v0q;
+        v = vp[k]; z = clampd(v, plo - off, phi - off); r1p[e] = rho * d.rp[k] * (v - z) - FY[k + 1];
+      }
+    }
+  }
+  suffix_sum<EPL>(r1v, lane);
+  suffix_sum<EPL>(r1p, lane);
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) r2p[e] = r1p[e];
+  suffix_sum<EPL>(r2p, lane);
+  const double mu0 = d.mu[((size_t)b * d.Qs + q) * 2], mu1 = d.mu[((size_t)b * d.Qs + q) * 2 + 1];
+  double du = 0.0, nd = 0.0, last = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int k = lane + 32 * e;
+    double prev = __shfl_up_sync(0xffffffffu, wj[e], 1);
+    if (lane == 0) prev = last;
+    last = __shfl_sync(0xffffffffu, wj[e], 31);
+    if (k < K) {
+      const double o = wa[e] + (prev - wj[e]) * ih + h * r1v[e] + h * h * (r2p[e] - 0.5 * r1p[e]) + 2.0 * xo[e] + h * mu0 +
+                       h * h * ((double)(K - 1 - k) + 0.5) * mu1;
+      du = fmax(du, fabs(o));
+      nd = fmax(nd, fmax(fabs(2.0 * xo[e]), fabs(o - 2.0 * xo[e])));
+    }
+  }
+  du = warp_max_nan(fabs(du)); nd = warp_max_nan(fabs(nd));
+  dn = warp_sum(dn); pn = warp_sum(pn); ob = warp_sum(ob);
+  if (lane == 0) {
+    atomic_max_pos(d.slab + (size_t)b * NRED + R_DUA, du); atomic_max_pos(d.slab + (size_t)b * NRED + R_NDUA, nd);
+    double* qs = d.qsum + ((size_t)b * d.Qs + q) * 3;
+    qs[0] = dn; qs[1] = pn; qs[2] = ob;
+  }
+}
+
+// deterministic per-rank sums of the per-agent-axis partials: one warp per scenario
+__global__ void k_local_sums(const __grid_constant__ Dev d) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= d.B) return;
+  if (d.st[b].phase >= 2) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int q = 2 * d.a_lo + lane; q < 2 * d.a_hi; q += 32) {
+    const double* qs = d.qsum + ((size_t)b * d.Qs + q) * 3;
+    s0 += qs[0]; s1 += qs[1]; s2 += qs[2];
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { double* sl = d.slab + (size_t)b * NRED; sl[R_DN] = s0; sl[R_PN] = s1; sl[R_OBJ] = s2; }
+}
+
+// ---------------------------------------------------------------------------------- collision rows
+// One thread per (scenario, own agent i, step k >= 1), k fastest: walks the candidate rows of (k, i), updates the
+// row multipliers (both owners keep identical copies) and sums the force on p_i[k]  (scp_device.inl collision_rows).
+template <int CHK>
+__global__ void __launch_bounds__(256) k_collide(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (S.phase != 1) return;
+  const int K = d.K, Nown = d.a_hi - d.a_lo;
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  double worst = 0.0;
+  if (tl < Nown * K) {
+    const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
+    if (k >= 1) {
+      const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
+      const double* Pb = d.P + (size_t)b * d.Qs * K;
+      const double pix = Pb[(size_t)(2 * i) * K + k], piy = Pb[(size_t)(2 * i + 1) * K + k];
+      const double rc = S.rho * d.rc[k - 1];
+      const int n = d.cnt[t];
+      double fx = 0, fy = 0, yx = 0, yy = 0;
+      for (int s = 0; s < n; ++s) {
+        const size_t o = (size_t)s * T + t;
+        const int j = d.cj[o];
+        const double ex = d.cex[o], ey = d.cey[o];
+        const double g = ex * (pix - Pb[(size_t)(2 * j) * K + k]) + ey * (piy - Pb[(size_t)(2 * j + 1) * K + k]);
+        const double l0 = d.lam[o];
+        const double l1 = fmax(0.0, l0 + 0.5 * rc * (d.cb[o] - g));
+        d.lam[o] = l1;
+        const double f = 2.0 * l1 - l0;
+        fx += f * ex; fy += f * ey;
+        if (CHK) { yx += l1 * ex; yy += l1 * ey; worst = fmax(worst, fabs(l1 - l0) / rc); }
+      }
+      const size_t r0 = ((size_t)b * d.Qs + 2 * i) * K + k;
+      d.F[r0] = fx; d.F[r0 + K] = fy;
+      if (CHK) { d.FY[r0] = yx; d.FY[r0 + K] = yy; }
+    }
+  }
+  if (CHK) {
+    worst = warp_max_nan(fabs(worst));
+    if ((threadIdx.x & 31) == 0 && worst > 0.0) atomic_max_pos(d.slab + (size_t)b * NRED + R_PRICOL, worst);
+  }
+}
+
+// ---------------------------------------------------------------------------------- snapshot / candidates
+__global__ void k_snapshot(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  if (!(d.st[b].flags & FL_SNAPSHOT)) return;
+  const size_t base = (size_t)b * d.Qs * d.K;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.Qs * d.K; e += gridDim.x * blockDim.x) {
+    d.Pbar[base + e] = d.P[base + e];
+    d.xprev[base + e] = d.x[base + e];
+  }
+}
+
+__device__ __forceinline__ void linearise_pair(double dx, double dy, int i, int j, double R, double& ex, double& ey, double& bound) {
+  // scp.py:498-509, 547-549; the degenerate branch draws a random direction there, a fixed one here
+  const double dist = hypot(dx, dy);
+  if (dist < 1e-6) { ex = i < j ? 1.0 : -1.0; ey = 0.0; bound = R + (ex * dx + ey * dy - 1.0); }
+  else { ex = dx / dist; ey = dy / dist; bound = R + ((ex * dx + ey * dy) - dist); }
+}
+
+// Candidate rows of (k, i): partners whose linearisation-point distance is below R + margin.  A rebuild (FL_KEEP,
+// after a verification failure enlarged the margin) keeps the multipliers of the rows already carried.
+__global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (!(S.flags & FL_BUILD)) return;
+  const int keep = S.flags & FL_KEEP;
+  const int K = d.K, N = d.N, Nown = d.a_hi - d.a_lo;
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  int mx = 0, over = 0;
+  if (tl < Nown * K) {
+    const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
+    if (k >= 1) {
+      const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
+      int oj[MAXC_MAX];
+      double ol[MAXC_MAX];
+      int on = 0;
+      if (keep) { on = d.cnt[t]; for (int s = 0; s < on; ++s) { oj[s] = d.cj[(size_t)s * T + t]; ol[s] = d.lam[(size_t)s * T + t]; } }
+      const double* Pb = d.Pbar + (size_t)b * d.Qs * K;
+      const double pix = Pb[(size_t)(2 * i) * K + k], piy = Pb[(size_t)(2 * i + 1) * K + k];
+      const double R = d.pb.min_distance, r2 = (R + S.margin) * (R + S.margin);
+      int n = 0;
+      for (int j = 0; j < N; ++j) {
+        if (j == i) continue;
+        const double dx = pix - Pb[(size_t)(2 * j) * K + k], dy = piy - Pb[(size_t)(2 * j + 1) * K + k];
+        if (dx * dx + dy * dy < r2) {
+          if (n < d.maxc) {
+            double ex, ey, bound, l = 0.0;
+            linearise_pair(dx, dy, i, j, R, ex, ey, bound);
+            for (int s = 0; s < on; ++s) if (oj[s] == j) l = ol[s];
+            const size_t o = (size_t)n * T + t;
+            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = l;
+            ++n;
+          } else over = 1;
+        }
+      }
+      d.cnt[t] = n; mx = n;
+      if (!keep) {
+        const size_t r0 = ((size_t)b * d.Qs + 2 * i) * K + k;
+        d.F[r0] = 0.0; d.F[r0 + K] = 0.0; d.FY[r0] = 0.0; d.FY[r0 + K] = 0.0;
+      }
+    }
+  }
+  double nc = warp_sum((double)mx);
+  double m = warp_max((double)mx), ov = warp_max((double)over);
+  if ((threadIdx.x & 31) == 0) {
+    double* sl = d.slab + (size_t)b * NRED;
+    if (m > 0.0) atomic_max_pos(sl + R_COPIES, m);
+    if (nc > 0.0) atomicAdd(sl + R_NCAND, nc);      // integer valued: exact in any order
+    if (ov > 0.0) atomic_max_pos(sl + R_OVER, ov);
+  }
+}
+
+// ---------------------------------------------------------------------------------- pair scan
+// One thread per (scenario, own agent i, step k): all partners j.  Always: min separation of the current positions
+// (scp.py:597-615 quantity).  FL_GATE: first row (k-major, i<j) below R - margin.  FL_VERIFY: every row of the full
+// QP that is NOT carried is evaluated; violated rows are counted and the margin that would carry them is reduced.
+__global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (!(S.flags & FL_SCAN)) return;
+  const int gate = S.flags & FL_GATE, verify = S.flags & FL_VERIFY;
+  const int K = d.K, N = d.N, Nown = d.a_hi - d.a_lo;
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  double mn = INFINITY, fr = INFINITY, bad = 0.0, maxd = 0.0;
+  if (tl < Nown * K) {
+    const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
+    const double* Pc = d.P + (size_t)b * d.Qs * K;
+    const double* Pb = d.Pbar + (size_t)b * d.Qs * K;
+    const double px = Pc[(size_t)(2 * i) * K + k], py = Pc[(size_t)(2 * i + 1) * K + k];
+    const double bx = Pb[(size_t)(2 * i) * K + k], by = Pb[(size_t)(2 * i + 1) * K + k];
+    const double R = d.pb.min_distance, thr = R - d.pb.feas_margin, r2 = (R + S.margin) * (R + S.margin), tol = d.pb.verify_tol;
+    const double npairs = (double)N * (double)(N - 1) * 0.5;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const double cx = px - Pc[(size_t)(2 * j) * K + k], cy = py - Pc[(size_t)(2 * j + 1) * K + k];
+      const double dd = sqrt(cx * cx + cy * cy);           // np.linalg.norm of a 2-vector
+      mn = fmin(mn, dd);
+      if (gate && j > i && dd < thr) {
+        const double rowi = (double)k * npairs + (double)(((long long)i * (2 * N - i - 1)) / 2 + (j - i - 1));
+        fr = fmin(fr, rowi);
+      }
+      if (verify && k >= 1) {
+        const double dx = bx - Pb[(size_t)(2 * j) * K + k], dy = by - Pb[(size_t)(2 * j + 1) * K + k];
+        const double d2 = dx * dx + dy * dy;
+        if (!(d2 < r2)) {
+          double ex, ey, bound;
+          linearise_pair(dx, dy, i, j, R, ex, ey, bound);
+          if (ex * cx + ey * cy < bound - tol) { bad += 1.0; maxd = fmax(maxd, sqrt(d2)); }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+    fr = fmin(fr, __shfl_xor_sync(0xffffffffu, fr, s));
+    bad += __shfl_xor_sync(0xffffffffu, bad, s);
+    maxd = fmax(maxd, __shfl_xor_sync(0xffffffffu, maxd, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    double* sl = d.slab + (size_t)b * NRED;
+    if (mn < INFINITY) atomic_min_pos(sl + R_MINSEP, mn);
+    if (fr < INFINITY) atomic_min_pos(sl + R_FIRST, fr);
+    if (bad > 0.0) { atomicAdd(sl + R_BAD, bad); atomic_max_pos(sl + R_MAXD, maxd); }
+  }
+}
+
+// ---------------------------------------------------------------------------------- rho rescale
+// keep y when rho changes: v = z + y/rho  ->  v = z + (v - z)/est   (scp_device.inl admm_run)
+__global__ void k_rescale(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  const State& S = d.st[b];
+  if (!(S.flags & FL_RESCALE)) return;
+  const int K = d.K, nq = 2 * (d.a_hi - d.a_lo);
+  const double est = S.est, h = d.pb.time_step;
+  const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nq * K; e += gridDim.x * blockDim.x) {
+    const int ql = e / K, k = e - ql * K, q = 2 * d.a_lo + ql;
+    const size_t o = ((size_t)b * d.Qs + q) * K + k;
+    double v = d.va[o], z = clampd(v, -al, al); d.va[o] = z + (v - z) / est;
+    if (k < K - 1) {
+      const double v0q = d.v0[(size_t)b * d.Q + q], p0q = d.p0[(size_t)b * d.Q + q];
+      const double off = p0q + h * (double)(k + 1) * v0q;
+      v = d.vj[o]; z = clampd(v, -jl, jl); d.vj[o] = z + (v - z) / est;
+      v = d.vv[o]; z = clampd(v, -vl - v0q, vl - v0q); d.vv[o] = z + (v - z) / est;
+      v = d.vp[o]; z = clampd(v, d.pb.space[q & 1] - off, d.pb.space[2 + (q & 1)] - off); d.vp[o] = z + (v - z) / est;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- outputs
+// scp.py:168-175: accelerations, positions, velocities of states k = 0..K-1, reference layout (N, K, 2).
+__global__ void k_output(const __grid_constant__ Dev d) {
+  const int b = blockIdx.y;
+  if (!(d.st[b].flags & FL_FINISH)) return;
+  const int K = d.K;
+  const int q = 2 * d.a_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * d.a_hi) return;
+  const size_t row = ((size_t)b * d.Qs + q) * K;
+  const double v0q = d.v0[(size_t)b * d.Q + q], h = d.pb.time_step;
+  const int i = q >> 1, ax = q & 1;
+  double c1 = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = (((size_t)b * d.Npad + i) * K + k) * 2 + ax;
+    const double xk = d.x[row + k];
+    d.acc[o] = xk;
+    d.pos[o] = d.P[row + k];
+    d.vel[o] = v0q + h * c1;
+    c1 += xk;
+  }
+}
+
+// ---------------------------------------------------------------------------------- control
+__device__ double combine(const Dev& d, int b, int slot, int kind) {   // kind 0 max, 1 sum, 2 min; fixed rank order
+  double r = kind == 2 ? INFINITY : 0.0;
+  for (int g = 0; g < d.G; ++g) {
+    const double v = d.gath[((size_t)g * d.B + b) * NRED + slot];
+    if (kind == 0) { if (!(v <= r)) r = v; }            // NaN wins
+    else if (kind == 1) r += v;
+    else r = fmin(r, v);
+  }
+  return r;
+}
+
+__device__ void start_qp(State& S, const Dev& d) {
+  S.qp_it = 0; S.it_mark = 0; S.pri_mark = INFINITY; S.stalled = 0; S.qp_solved = 0;
+}
+
+// after the check iteration: ADMM termination test of the running subproblem (OSQP's, in reference units)
+__global__ void k_control1(const __grid_constant__ Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  State& S = d.st[b];
+  if (S.phase >= 2) return;
+  double pri = combine(d, b, R_PRI, 0);
+  const double pc = combine(d, b, R_PRICOL, 0);
+  if (!(pc <= pri)) pri = pc;
+  const double npri = combine(d, b, R_NPRI, 0), dua = combine(d, b, R_DUA, 0), ndua = combine(d, b, R_NDUA, 0);
+  S.dn = combine(d, b, R_DN, 1); S.pn = combine(d, b, R_PN, 1); S.obj = combine(d, b, R_OBJ, 1);
+  double* sl = d.slab + (size_t)b * NRED;
+  for (int s = 0; s <= R_OBJ; ++s) sl[s] = 0.0;
+  const int check = d.pb.check_every, maxit = d.pb.max_admm_iter;
+  S.qp_it += check;
+  scp_b200_record& r = d.rec[b];
+  r.admm_iterations += check;
+  if (S.phase == 1) r.cand_row_iters += 0.5 * S.ncand * (double)check;
+  S.pri = pri; S.dua = dua;
+  const double ea = d.pb.eps_abs, er = d.pb.eps_rel;
+  const int nan = !(pri == pri) || !(dua == dua);
+  const int solved = !nan && pri <= ea + er * npri && dua <= ea + er * ndua;
+  int stalled = 0;
+  if (!solved && !nan && d.pb.stall_window > 0 && S.qp_it - S.it_mark >= d.pb.stall_window) {
+    if (pri > 1e-3 * (1.0 + npri) && pri > 0.8 * S.pri_mark) stalled = 1;
+    else { S.it_mark = S.qp_it; S.pri_mark = pri; }
+  }
+  if (solved || nan || stalled || S.qp_it >= maxit) {
+    S.qp_solved = solved; S.stalled = stalled;
+    const double full = (double)d.N * (double)(d.N - 1) * (double)(d.K - 1);
+    S.flags |= FL_SCAN | (S.phase == 0 ? FL_GATE : ((solved && S.ncand < full) ? FL_VERIFY : 0));
+  } else if (d.pb.adapt_every > 0 && S.qp_it % d.pb.adapt_every == 0) {
+    double est = sqrt((pri / fmax(npri, 1e-12)) / fmax(dua / fmax(ndua, 1e-12), 1e-12));
+    if (est > 5.0 || est < 0.2) {
+      est = clampd(est, 1e-2, 1e2);
+      const double nrho = clampd(S.rho * est, 1e-6, 1e6);
+      S.est = nrho / S.rho; S.rho = nrho;
+      S.flags |= FL_RESCALE | FL_FACTOR;
+    }
+  }
+}
+
+// after the pair scan: end of a subproblem -> gate (scp.py:144), candidate enlargement, or the SCP bookkeeping
+// of scp.py:157-166
+__global__ void k_control2(const __grid_constant__ Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  State& S = d.st[b];
+  if (S.phase >= 2 || !(S.flags & FL_SCAN)) return;
+  const double minsep = combine(d, b, R_MINSEP, 2), first = combine(d, b, R_FIRST, 2);
+  const double bad = combine(d, b, R_BAD, 1), maxd = combine(d, b, R_MAXD, 0);
+  double* sl = d.slab + (size_t)b * NRED;
+  sl[R_MINSEP] = INFINITY; sl[R_FIRST] = INFINITY; sl[R_BAD] = 0.0; sl[R_MAXD] = 0.0;
+  scp_b200_record& r = d.rec[b];
+  S.minsep = minsep;
+  r.pri_res = S.pri; r.dua_res = S.dua;
+  int finish = 0, next_iter = 0;
+  if (S.phase == 0) {
+    if (!S.qp_solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; finish = 1; }
+    const int feasible = !(first < INFINITY);
+    r.initial_feasible = feasible;
+    if (!feasible) {
+      const int N = d.N, K = d.K;
+      const long long np = (long long)N * (N - 1) / 2, fl = (long long)first;
+      const int k = (int)(fl / np);
+      long long p = fl - (long long)k * np;
+      int i = 0;
+      while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
+      const int j = i + 1 + (int)p;
+      r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = j;
+      const double* Pc = d.P + (size_t)b * d.Qs * K;
+      const double dx = Pc[(size_t)(2 * i) * K + k] - Pc[(size_t)(2 * j) * K + k], dy = Pc[(size_t)(2 * i + 1) * K + k] - Pc[(size_t)(2 * j + 1) * K + k];
+      r.first_violation_dist = sqrt(dx * dx + dy * dy);
+      if (k == 0 && r.status == SCP_B200_STATUS_OK) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
+    }
+    if (feasible || d.pb.max_scp_iter <= 0) finish = 1;
+    if (!finish) next_iter = 1;
+  } else {
+    if (S.qp_solved && (S.flags & FL_VERIFY) && bad > 0.0 && S.attempt < 20) {
+      r.rebuilds++; S.attempt++;
+      const double need = (maxd - d.pb.min_distance) * (1.0 + 1e-9) + 1e-9;
+      S.margin = fmax(S.margin * (1.0 + 1e-9), need);
+      S.flags |= FL_BUILD | FL_KEEP;
+      start_qp(S, d);
+    } else {
+      if (!S.qp_solved) { r.qp_unsolved++; if (S.stalled) r.qp_infeasible++; }
+      const double rel = sqrt(S.dn) / sqrt(S.pn);
+      if (S.scp_it < SCP_B200_MAX_SCP_ITER) r.rel_step[S.scp_it] = rel;
+      const int conv = rel <= d.pb.scp_tolerance;
+      S.scp_it++;
+      r.scp_iterations = S.scp_it; r.converged = conv;
+      if (conv || S.scp_it >= d.pb.max_scp_iter) finish = 1; else next_iter = 1;
+    }
+  }
+  if (finish) {
+    r.min_separation = minsep; r.objective = S.obj;
+    S.flags |= FL_FINISH;
+  } else if (next_iter) {
+    S.phase = 1; S.rho = d.pb.rho0; S.margin = d.pb.cand_margin; S.attempt = 0; S.have_state = 0;
+    S.flags |= FL_SNAPSHOT | FL_BUILD | FL_RESET;
+    start_qp(S, d);
+  }
+}
+
+// after the candidate build: copies (the operator's collision weight) and whether the operator must be rebuilt
+__global__ void k_control3(const __grid_constant__ Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  State& S = d.st[b];
+  if (S.phase >= 2 || !(S.flags & FL_BUILD)) return;
+  const int copies = (int)combine(d, b, R_COPIES, 0);
+  const double ncand = combine(d, b, R_NCAND, 1), over = combine(d, b, R_OVER, 0);
+  double* sl = d.slab + (size_t)b * NRED;
+  sl[R_COPIES] = 0.0; sl[R_NCAND] = 0.0; sl[R_OVER] = 0.0;
+  scp_b200_record& r = d.rec[b];
+  if (over > 0.0) r.reserved2 |= 4;                 // candidate capacity exceeded: rows were dropped (reported by the host)
+  if (!S.have_state || copies != S.copies) S.flags |= FL_FACTOR;
+  S.copies = copies; S.ncand = ncand; S.have_state = 1;
+  if (copies > r.max_copies) r.max_copies = copies;
+}
+
+__global__ void k_finalize(const __grid_constant__ Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  State& S = d.st[b];
+  if (S.phase < 2 && (S.flags & FL_FINISH)) { S.phase = 2; atomicAdd(d.done, 1); }
+  S.flags = 0;
+}
+
+// ---------------------------------------------------------------------------------- host side
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.handle ? &api : nullptr;
+  tried = true;
+  const char* env = getenv("SCP_B200_NCCL_LIB");
+  void* h = env ? dlopen(env, RTLD_NOW | RTLD_GLOBAL) : nullptr;
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);   // the copy PyTorch already loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+  api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) return nullptr;
+  api.handle = h;
+  return &api;
+}
+
+}  // namespace ss
+
+struct scp_b200_stream {
+  ss::Dev d;
+  std::vector<void*> allocs;
+  ncclComm_t comm = nullptr;
+  int* h_done = nullptr;          // pinned, 2 entries
+  cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
+  void* tables = nullptr;
+  void* io = nullptr;             // device staging of the host-buffer entry point
+  size_t io_bytes = 0;
+  int qpc = 8, nblk_q = 1, epl = 1;
+  size_t smem_axis = 0, smem_factor = 0;
+  long long macro_steps = 0;
+};
+
+namespace {
+
+#define SS_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) return scp_b200_set_error(100 + (int)_e, (std::string(#expr) + ": " + cudaGetErrorString(_e)).c_str()); \
+  } while (0)
+#define SS_NCCL(expr)                                                                                      \
+  do {                                                                                                     \
+    ncclResult_t _r = (expr);                                                                              \
+    if (_r != ncclSuccess) return scp_b200_set_error(300 + (int)_r, (std::string(#expr) + ": " + (api->GetErrorString ? api->GetErrorString(_r) : "nccl error")).c_str()); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(scp_b200_stream* s, T** p, size_t n) {
+  void* q = nullptr;
+  SS_CUDA(cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  s->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+template <int MODE>
+void launch_axis(scp_b200_stream* s, cudaStream_t st) {
+  const ss::Dev& d = s->d;
+  dim3 grid(s->nblk_q, d.B);
+  const size_t smem = (MODE <= 1 ? (size_t)d.K * d.K : 0) * sizeof(double) + (size_t)(ss::AX_THREADS / 32) * d.K * sizeof(double);
+  switch (s->epl) {
+    case 1: ss::k_axis<1, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
+    case 2: ss::k_axis<2, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
+    case 3: ss::k_axis<3, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
+    default: ss::k_axis<4, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
+  }
+}
+
+void launch_dual(scp_b200_stream* s, cudaStream_t st) {
+  const ss::Dev& d = s->d;
+  const int nq = 2 * (d.a_hi - d.a_lo);
+  dim3 grid((nq * 32 + ss::AX_THREADS - 1) / ss::AX_THREADS, d.B);
+  switch (s->epl) {
+    case 1: ss::k_dual<1><<<grid, ss::AX_THREADS, 0, st>>>(d); break;
+    case 2: ss::k_dual<2><<<grid, ss::AX_THREADS, 0, st>>>(d); break;
+    case 3: ss::k_dual<3><<<grid, ss::AX_THREADS, 0, st>>>(d); break;
+    default: ss::k_dual<4><<<grid, ss::AX_THREADS, 0, st>>>(d); break;
+  }
+}
+
+template <typename F>
+void set_axis_smem(F f, size_t smem) { cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+
+}  // namespace
+
+extern "C" {
+
+int scp_b200_nccl_unique_id(void* id128) {
+  ss::NcclApi* api = ss::nccl_api();
+  if (!api) return scp_b200_set_error(3, "libnccl.so.2 not found (set SCP_B200_NCCL_LIB)");
+  ncclUniqueId id;
+  SS_NCCL(api->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+void scp_b200_stream_destroy(scp_b200_stream* s) {
+  if (!s) return;
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->h_done) cudaFreeHost(s->h_done);
+  if (s->io) cudaFree(s->io);
+  for (auto e : {s->ev[0], s->ev[1], s->t0, s->t1}) if (e) cudaEventDestroy(e);
+  if (s->comm) { ss::NcclApi* api = ss::nccl_api(); if (api) api->CommDestroy(s->comm); }
+  delete s;
+}
+
+int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int max_candidates, int rank, int world,
+                           const void* nccl_id128, scp_b200_stream** out) {
+  if (!prob || !out) return scp_b200_set_error(1, "null argument");
+  *out = nullptr;
+  const int N = prob->n_agents, K = prob->n_steps, B = n_scenarios;
+  if (N < 1 || K < 2 || B < 1) return scp_b200_set_error(1, "bad sizes");
+  if (K > 128) return scp_b200_set_error(1, "streaming solver: n_steps must be <= 128");
+  if (B > 65535) return scp_b200_set_error(1, "streaming solver: at most 65535 scenarios per call");
+  if (world < 1 || rank < 0 || rank >= world) return scp_b200_set_error(1, "bad rank/world");
+  if (world > 1 && B != 1) return scp_b200_set_error(1, "agent sharding (world > 1) solves ONE scenario; shard batches by scenario instead");
+  if (world > 1 && !nccl_id128) return scp_b200_set_error(1, "world > 1 needs an NCCL unique id");
+  if (prob->check_every < 1 || prob->max_admm_iter < 1 || !(prob->time_step > 0)) return scp_b200_set_error(1, "bad ADMM settings");
+  if (max_candidates <= 0) max_candidates = 16;
+  if (max_candidates > ss::MAXC_MAX) max_candidates = ss::MAXC_MAX;
+  if (max_candidates > N - 1) max_candidates = N > 1 ? N - 1 : 1;
+  scp_b200_stream* s = new scp_b200_stream();
+  ss::Dev& d = s->d;
+  memset(&d, 0, sizeof(d));
+  d.pb = *prob;
+  d.pb.max_admm_iter = ((prob->max_admm_iter + prob->check_every - 1) / prob->check_every) * prob->check_every;
+  d.B = B; d.N = N; d.K = K; d.Q = 2 * N; d.G = world; d.rank = rank; d.maxc = max_candidates;
+  const int nper = (N + world - 1) / world;
+  d.Npad = nper * world; d.Qs = 2 * d.Npad;
+  d.a_lo = rank * nper < N ? rank * nper : N;
+  d.a_hi = (rank + 1) * nper < N ? (rank + 1) * nper : N;
+  const int Nown = d.a_hi - d.a_lo;
+  int rc = 0;
+  auto fail = [&](int code) { scp_b200_stream_destroy(s); return code; };
+  // tables
+  scp::HostTables t = scp::build_host_tables(d.pb);
+  double* tb = nullptr;
+  if ((rc = dev_alloc(s, &tb, t.blob.size()))) return fail(rc);
+  if (cudaMemcpy(tb, t.blob.data(), t.blob.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail(scp_b200_set_error(100, "table upload failed"));
+  d.B1 = tb; d.B2 = tb + (size_t)K * K; d.rj = tb + 2 * (size_t)K * K; d.ra = d.rj + K; d.rv = d.ra + K; d.rp = d.rv + K; d.rc = d.rp + K;
+  const size_t QK = (size_t)B * d.Qs * K;
+  double** arrs[] = {&d.x, &d.xprev, &d.va, &d.vj, &d.vv, &d.vp, &d.P, &d.Pbar, &d.F, &d.FY};
+  for (double** a : arrs) if ((rc = dev_alloc(s, a, QK))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.mu, (size_t)B * d.Qs * 2))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.qsum, (size_t)B * d.Qs * 3))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.Nmat, (size_t)B * K * K))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.N0, (size_t)B * 2 * K))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.Qm, (size_t)B * 2 * K))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.gg, (size_t)B * 4))) return fail(rc);
+  const size_t T = (size_t)B * (Nown > 0 ? Nown : 1) * K;
+  if ((rc = dev_alloc(s, &d.cnt, T))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.cj, T * d.maxc))) return fail(rc);
+  double** carr[] = {&d.cex, &d.cey, &d.cb, &d.lam};
+  for (double** a : carr) if ((rc = dev_alloc(s, a, T * d.maxc))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.slab, (size_t)B * ss::NRED))) return fail(rc);
+  if (world > 1) { if ((rc = dev_alloc(s, &d.gath, (size_t)world * B * ss::NRED))) return fail(rc); }
+  else d.gath = d.slab;
+  if ((rc = dev_alloc(s, &d.st, (size_t)B))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.done, 1))) return fail(rc);
+  const size_t OUT = (size_t)B * d.Npad * K * 2;
+  if ((rc = dev_alloc(s, &d.acc, OUT))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.pos, OUT))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.vel, OUT))) return fail(rc);
+  if (cudaMallocHost((void**)&s->h_done, 2 * sizeof(int)) != cudaSuccess) return fail(scp_b200_set_error(100, "pinned allocation failed"));
+  for (cudaEvent_t* e : {&s->ev[0], &s->ev[1]}) if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail(scp_b200_set_error(100, "event"));
+  for (cudaEvent_t* e : {&s->t0, &s->t1}) if (cudaEventCreate(e) != cudaSuccess) return fail(scp_b200_set_error(100, "event"));
+  // launch geometry of the agent-axis kernel: about two CTAs per SM over the whole batch, >= 8 agent-axes per CTA
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nq = 2 * Nown;
+  int nb = (2 * sms + B - 1) / B;
+  const int nbmax = (nq + 7) / 8;
+  if (nb > nbmax) nb = nbmax;
+  if (nb < 1) nb = 1;
+  int qpc = (nq + nb - 1) / nb;
+  qpc = ((qpc + 7) / 8) * 8;
+  if (qpc < 8) qpc = 8;
+  s->qpc = qpc; s->nblk_q = nq > 0 ? (nq + qpc - 1) / qpc : 1;
+  s->epl = (K + 31) / 32;
+  s->smem_axis = ((size_t)K * K + (size_t)(ss::AX_THREADS / 32) * K) * sizeof(double);
+  s->smem_factor = ((size_t)K * K + 4 * (size_t)K) * sizeof(double);
+  set_axis_smem(ss::k_axis<1, 0>, s->smem_axis); set_axis_smem(ss::k_axis<1, 1>, s->smem_axis);
+  set_axis_smem(ss::k_axis<2, 0>, s->smem_axis); set_axis_smem(ss::k_axis<2, 1>, s->smem_axis);
+  set_axis_smem(ss::k_axis<3, 0>, s->smem_axis); set_axis_smem(ss::k_axis<3, 1>, s->smem_axis);
+  set_axis_smem(ss::k_axis<4, 0>, s->smem_axis); set_axis_smem(ss::k_axis<4, 1>, s->smem_axis);
+  set_axis_smem(ss::k_factor, s->smem_factor);
+  if (world > 1) {
+    ss::NcclApi* api = ss::nccl_api();
+    if (!api) return fail(scp_b200_set_error(3, "libnccl.so.2 not found (set SCP_B200_NCCL_LIB)"));
+    ncclUniqueId id;
+    memcpy(&id, nccl_id128, sizeof(id));
+    ncclResult_t r = api->CommInitRank(&s->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(scp_b200_set_error(300 + (int)r, "ncclCommInitRank failed"));
+  }
+  *out = s;
+  return 0;
+}
+
+// The whole of SCP.generate_trajectories (scp.py:131-180) for the solver's B scenarios (or for ONE scenario whose
+// agents are sharded over `world` ranks: every rank calls this with the same inputs).  Blocks until finished.
+int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* d_v0, const double* d_pf, const double* d_vf,
+                          double* d_acc, double* d_pos, double* d_vel, scp_b200_record* d_records, void* stream,
+                          float* device_ms, int64_t* macro_steps) {
+  if (!s) return scp_b200_set_error(1, "null solver");
+  ss::Dev& d = s->d;
+  ss::NcclApi* api = ss::nccl_api();
+  cudaStream_t st = (cudaStream_t)stream;
+  d.p0 = d_p0; d.v0 = d_v0; d.pf = d_pf; d.vf = d_vf; d.rec = d_records;
+  const int B = d.B, K = d.K, Nown = d.a_hi - d.a_lo, G = d.G;
+  const dim3 g_elem((d.Qs * K + 255) / 256 < 64 ? (d.Qs * K + 255) / 256 : 64, B);
+  const dim3 g_ik((Nown * K + 255) / 256 > 0 ? (Nown * K + 255) / 256 : 1, B);
+  const dim3 g_b((B + 127) / 128);
+  const size_t pslice = (size_t)(d.Qs / G) * K;            // doubles per rank in the position all-gather (B == 1 when G > 1)
+  auto gather_positions = [&]() -> int {
+    if (G > 1) SS_NCCL(api->AllGather(d.P + (size_t)d.rank * pslice, d.P, pslice, ncclFloat64, s->comm, st));
+    return 0;
+  };
+  auto exchange = [&]() -> int {
+    if (G > 1) SS_NCCL(api->AllGather(d.slab, d.gath, (size_t)B * ss::NRED, ncclFloat64, s->comm, st));
+    return 0;
+  };
+  SS_CUDA(cudaEventRecord(s->t0, st));
+  ss::k_init<<<g_elem, 256, 0, st>>>(d);
+  ss::k_factor<<<B, 512, s->smem_factor, st>>>(d);
+  ss::k_finalize<<<g_b, 128, 0, st>>>(d);
+  SS_CUDA(cudaGetLastError());
+  const int check = d.pb.check_every;
+  const long long max_macros = (long long)(d.pb.max_scp_iter + 2) * 22 * (d.pb.max_admm_iter / check + 2);
+  s->h_done[0] = s->h_done[1] = 0;
+  int rc = 0;
+  auto macro = [&](long long m) -> int {
+    for (int it = 1; it < check; ++it) {
+      launch_axis<0>(s, st);
+      if ((rc = gather_positions())) return rc;
+      ss::k_collide<0><<<g_ik, 256, 0, st>>>(d);
+    }
+    launch_axis<1>(s, st);
+    if ((rc = gather_positions())) return rc;
+    ss::k_collide<1><<<g_ik, 256, 0, st>>>(d);
+    launch_dual(s, st);
+    ss::k_local_sums<<<(B * 32 + 127) / 128, 128, 0, st>>>(d);
+    if ((rc = exchange())) return rc;
+    ss::k_control1<<<g_b, 128, 0, st>>>(d);
+    ss::k_scan<<<g_ik, 256, 0, st>>>(d);
+    if ((rc = exchange())) return rc;
+    ss::k_control2<<<g_b, 128, 0, st>>>(d);
+    ss::k_snapshot<<<g_elem, 256, 0, st>>>(d);
+    ss::k_build<<<g_ik, 256, 0, st>>>(d);
+    if ((rc = exchange())) return rc;
+    ss::k_control3<<<g_b, 128, 0, st>>>(d);
+    ss::k_rescale<<<g_elem, 256, 0, st>>>(d);
+    launch_axis<2>(s, st);
+    ss::k_factor<<<B, 512, s->smem_factor, st>>>(d);
+    ss::k_output<<<dim3((2 * Nown + 127) / 128 > 0 ? (2 * Nown + 127) / 128 : 1, B), 128, 0, st>>>(d);
+    ss::k_finalize<<<g_b, 128, 0, st>>>(d);
+    SS_CUDA(cudaMemcpyAsync(&s->h_done[m & 1], d.done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaEventRecord(s->ev[m & 1], st));
+    return 0;
+  };
+  long long m = 0;
+  if ((rc = macro(0))) return rc;
+  for (;;) {
+    if ((rc = macro(m + 1))) return rc;
+    SS_CUDA(cudaEventSynchronize(s->ev[m & 1]));
+    if (s->h_done[m & 1] >= B) break;
+    ++m;
+    if (m > max_macros) return scp_b200_set_error(4, "streaming solver: macro step limit reached");
+  }
+  s->macro_steps = m + 1;
+  // outputs: own agents were written by k_output; a sharded solve gathers the agent blocks (agent-major layout)
+  const size_t oslice = (size_t)(d.Npad / G) * K * 2;
+  if (G > 1) {
+    for (double* o : {d.acc, d.pos, d.vel}) SS_NCCL(api->AllGather(o + (size_t)d.rank * oslice, o, oslice, ncclFloat64, s->comm, st));
+  }
+  const size_t row = (size_t)d.N * K * 2 * sizeof(double);
+  if (d.Npad == d.N) {
+    if (d_acc) SS_CUDA(cudaMemcpyAsync(d_acc, d.acc, row * B, cudaMemcpyDeviceToDevice, st));
+    if (d_pos) SS_CUDA(cudaMemcpyAsync(d_pos, d.pos, row * B, cudaMemcpyDeviceToDevice, st));
+    if (d_vel) SS_CUDA(cudaMemcpyAsync(d_vel, d.vel, row * B, cudaMemcpyDeviceToDevice, st));
+  } else {
+    const size_t prow = (size_t)d.Npad * K * 2 * sizeof(double);
+    if (d_acc) SS_CUDA(cudaMemcpy2DAsync(d_acc, row, d.acc, prow, row, B, cudaMemcpyDeviceToDevice, st));
+    if (d_pos) SS_CUDA(cudaMemcpy2DAsync(d_pos, row, d.pos, prow, row, B, cudaMemcpyDeviceToDevice, st));
+    if (d_vel) SS_CUDA(cudaMemcpy2DAsync(d_vel, row, d.vel, prow, row, B, cudaMemcpyDeviceToDevice, st));
+  }
+  SS_CUDA(cudaEventRecord(s->t1, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_CUDA(cudaGetLastError());
+  if (device_ms) SS_CUDA(cudaEventElapsedTime(device_ms, s->t0, s->t1));
+  if (macro_steps) *macro_steps = s->macro_steps;
+  return 0;
+}
+
+// Same with host buffers (what a non-PyTorch caller or the reference's SCP class binds): copies in, solves, copies out.
+int scp_b200_stream_solve_host(scp_b200_stream* s, const double* h_p0, const double* h_v0, const double* h_pf,
+                               const double* h_vf, double* h_acc, double* h_pos, double* h_vel,
+                               scp_b200_record* h_records, float* device_ms, int64_t* macro_steps) {
+  if (!s) return scp_b200_set_error(1, "null solver");
+  const ss::Dev& d = s->d;
+  const size_t n2 = (size_t)d.B * d.N * 2 * sizeof(double), n3 = (size_t)d.B * d.N * d.K * 2 * sizeof(double);
+  const size_t nr = (size_t)d.B * sizeof(scp_b200_record);
+  const size_t need = 4 * n2 + 3 * n3 + nr + 256;
+  if (need > s->io_bytes) {
+    if (s->io) cudaFree(s->io);
+    s->io = nullptr; s->io_bytes = 0;
+    SS_CUDA(cudaMalloc(&s->io, need));
+    s->io_bytes = need;
+  }
+  char* io = (char*)s->io;
+  double *p0 = (double*)io, *v0 = (double*)(io + n2), *pf = (double*)(io + 2 * n2), *vf = (double*)(io + 3 * n2);
+  double *acc = (double*)(io + 4 * n2), *pos = (double*)(io + 4 * n2 + n3), *vel = (double*)(io + 4 * n2 + 2 * n3);
+  scp_b200_record* rec = (scp_b200_record*)(io + 4 * n2 + 3 * n3);
+  SS_CUDA(cudaMemcpy(p0, h_p0, n2, cudaMemcpyHostToDevice));
+  SS_CUDA(cudaMemcpy(v0, h_v0, n2, cudaMemcpyHostToDevice));
+  SS_CUDA(cudaMemcpy(pf, h_pf, n2, cudaMemcpyHostToDevice));
+  SS_CUDA(cudaMemcpy(vf, h_vf, n2, cudaMemcpyHostToDevice));
+  if (int rc = scp_b200_stream_solve(s, p0, v0, pf, vf, acc, pos, vel, rec, nullptr, device_ms, macro_steps)) return rc;
+  if (h_acc) SS_CUDA(cudaMemcpy(h_acc, acc, n3, cudaMemcpyDeviceToHost));
+  if (h_pos) SS_CUDA(cudaMemcpy(h_pos, pos, n3, cudaMemcpyDeviceToHost));
+  if (h_vel) SS_CUDA(cudaMemcpy(h_vel, vel, n3, cudaMemcpyDeviceToHost));
+  if (h_records) SS_CUDA(cudaMemcpy(h_records, rec, nr, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -124,6 +124,20 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "scp_b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "scp_b200_stream_create": (
+        C.c_int, [_P(Problem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_void_p)]),
+    "scp_b200_stream_destroy": (None, [C.c_void_p]),
+    "scp_b200_stream_solve": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, _P(C.c_float), _P(C.c_int64)],
+    ),
+    "scp_b200_stream_solve_host": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         _P(C.c_float), _P(C.c_int64)],
+    ),
     "scp_b200_linearize": (
         C.c_int,
         [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -192,5 +206,6 @@ def record_to_dict(r: Record) -> dict:
         cycles_peval=int(r.cycles_peval), cycles_papply=int(r.cycles_papply),
         first_violation_dist=float(r.first_violation_dist), min_separation=float(r.min_separation),
         objective=float(r.objective), pri_res=float(r.pri_res), dua_res=float(r.dua_res), cand_row_iters=float(r.cand_row_iters),
+        reserved2=int(r.reserved2),
         rel_steps=[float(r.rel_step[i]) for i in range(n)],
     )

@@ -164,6 +164,43 @@ int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents,
                              double min_distance, double feas_margin, int64_t pair_begin, int64_t pair_end,
                              double* d_eta, double* d_bound, double* d_minsep, int32_t* d_first, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Streaming solver: the same loop (scp.py:131-180) as a fixed sequence of HBM/L2-streaming kernels
+ * over all scenarios and agents, per-scenario control flow decided on the device.  Two uses:
+ *   world == 1 : a batch of B scenarios that are too large for one CTA's shared memory
+ *                (BASELINE.json configs 3 and 5: 50-200 agents);
+ *   world  > 1 : ONE scenario (B = 1) whose agents are sharded over the GPUs of a node
+ *                (config 4): rank g owns agents [g*ceil(N/world), ...), every ADMM iteration ends
+ *                with an NCCL all-gather of the positions (scp.py:463 is where the reference
+ *                recomputes them), residual scalars are all-gathered at check iterations.
+ * Subproblems end on the ADMM residual test (eps_abs/eps_rel of the problem), there is no polish.
+ * n_steps <= 128.  Records use the fields of scp_b200_record (cycles_* and polish_* stay 0;
+ * reserved2 bit 2 = the per-(step,agent) candidate capacity was exceeded). */
+typedef struct scp_b200_stream scp_b200_stream;
+
+/* 128-byte NCCL unique id (rank 0 creates it, the host side broadcasts it to the other ranks). */
+int scp_b200_nccl_unique_id(void* id128);
+
+/* max_candidates: collision rows carried per (step, agent), <= 48 (0: default 16).
+ * nccl_id128 may be NULL when world == 1.  The CUDA device current at this call owns the solver. */
+int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int max_candidates, int rank,
+                           int world, const void* nccl_id128, scp_b200_stream** out);
+void scp_b200_stream_destroy(scp_b200_stream* solver);
+
+/* Device buffers as in scp_b200_solve_batch; with world > 1 every rank passes the same full-size
+ * inputs and receives the full outputs.  Blocks until finished; *device_ms (optional) is the time
+ * between the first and the last operation on `stream`, *macro_steps the check periods run. */
+int scp_b200_stream_solve(scp_b200_stream* solver, const double* d_p0, const double* d_v0,
+                          const double* d_pf, const double* d_vf, double* d_acc, double* d_pos,
+                          double* d_vel, scp_b200_record* d_records, void* stream, float* device_ms,
+                          int64_t* macro_steps);
+
+/* Same with host buffers. */
+int scp_b200_stream_solve_host(scp_b200_stream* solver, const double* h_p0, const double* h_v0,
+                               const double* h_pf, const double* h_vf, double* h_acc, double* h_pos,
+                               double* h_vel, scp_b200_record* h_records, float* device_ms,
+                               int64_t* macro_steps);
+
 #ifdef __cplusplus
 }
 #endif

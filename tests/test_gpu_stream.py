@@ -1,0 +1,152 @@
+"""GPU parity tests of the streaming solver (scp_b200_stream_*, csrc/scp_stream.cu) through the C ABI.
+
+Same bar as test_gpu_parity.py: final positions <= 1e-3 relative and objective <= 1e-4 relative against the
+KKT-certified golden fixtures, identical pass/fail on the minimum-separation and dynamics-residual checks.
+The streaming solver ends its subproblems on the ADMM residual test (no polish), so agreement with the certified
+minimisers is to solver tolerance, not to rounding; the SCP iteration count must still be the reference's.
+"""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, OBJ_TOL, DYN_TOL = 1e-3, 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _solve(p0, pf, T, h, R, space, **kw):
+    from path_planning.solvers.stream import StreamSolver
+
+    p0 = np.asarray(p0, dtype=np.float64)
+    if p0.ndim == 2:
+        p0, pf = p0[None], np.asarray(pf)[None]
+    s = StreamSolver(p0.shape[1], T, h, R, space, n_scenarios=p0.shape[0], **kw)
+    traj, recs = s.solve(p0, pf)
+    ms = s.last_device_ms
+    s.close()
+    return traj, recs, ms
+
+
+@pytest.mark.parametrize("path", golden_cases())
+def test_stream_matches_golden(torch_cuda, path):
+    from oracle import scp_oracle
+
+    g = np.load(path)
+    N, h, R, space = int(g["N"]), float(g["h"]), float(g["R"]), list(g["space"])
+    traj, recs, ms = _solve(g["p0"], g["pf"], float(g["T"]), h, R, space)
+    r, pos, acc = recs[0], traj["positions"][0], traj["accelerations"][0]
+    assert r["status"] == 0 and r["qp_unsolved"] == 0
+    assert r["scp_iterations"] == int(g["iterations"])
+    assert r["initial_feasible"] == (int(g["iterations"]) == 0)
+    assert np.allclose(r["rel_steps"], g["rel_steps"], rtol=2e-2, atol=5e-4)
+    perr = np.linalg.norm(pos - g["positions"]) / np.linalg.norm(g["positions"])
+    oerr = abs(r["objective"] - float(g["objective"])) / float(g["objective"])
+    assert perr <= POS_TOL, perr
+    assert oerr <= OBJ_TOL, oerr
+    z = np.zeros((N, 2))
+    assert (r["min_separation"] >= R - 0.01) == (float(g["min_separation"]) >= R - 0.01)
+    assert abs(r["min_separation"] - scp_oracle.min_separation(pos)) <= 1e-12
+    assert abs(r["objective"] - (acc ** 2).sum()) <= 1e-9 * r["objective"]
+    dyn = scp_oracle.dynamics_residual(acc, g["p0"], z, g["pf"], z, h, space, positions=pos)
+    assert dyn <= DYN_TOL
+    loose = np.linalg.norm(g["loose_positions"] - g["positions"]) / np.linalg.norm(g["positions"])
+    print(f"{os.path.basename(path)}: stream pos err {perr:.1e} (loose reference {loose:.1e}), objective err {oerr:.1e}, "
+          f"ADMM iterations {r['admm_iterations']}, device {ms:.1f} ms")
+
+
+def test_stream_batch_equals_single(torch_cuda):
+    """Scenarios of a batch do not influence each other: batch results == one-by-one results, bit for bit."""
+    from path_planning.scenarios.position_generator import generate_positions
+
+    starts, goals = [], []
+    for b in range(6):
+        random.seed(200 + b)
+        p0, pf = generate_positions(8, 0.8)
+        starts.append(p0)
+        goals.append(pf)
+    starts, goals = np.stack(starts), np.stack(goals)
+    tb, rb, _ = _solve(starts, goals, 10.0, 0.2, 0.8, [0, 0, 20, 20])
+    for b in (0, 3, 5):
+        t1, r1, _ = _solve(starts[b], goals[b], 10.0, 0.2, 0.8, [0, 0, 20, 20])
+        assert np.array_equal(t1["positions"][0], tb["positions"][b])
+        assert r1[0]["admm_iterations"] == rb[b]["admm_iterations"] and r1[0]["scp_iterations"] == rb[b]["scp_iterations"]
+
+
+def test_stream_agrees_with_cta_solver_on_c2_scenarios(torch_cuda):
+    """32 of config 2's scenarios: wherever both solvers solved every subproblem, trajectories agree to tolerance
+    and the feasibility verdicts are the same."""
+    from oracle import scp_oracle
+    from path_planning.scenarios.position_generator import generate_positions
+    from path_planning.solvers.batch import BatchSolver
+
+    B, N, R, h = 32, 25, 0.8, 0.2
+    starts, goals = [], []
+    for b in range(B):
+        random.seed(10_000 + b)
+        p0, pf = generate_positions(N, R)
+        starts.append(p0)
+        goals.append(pf)
+    starts, goals = np.stack(starts), np.stack(goals)
+    ts, rs, _ = _solve(starts, goals, 10.0, h, R, [0, 0, 20, 20])
+    tc, rc = BatchSolver(N, 10.0, h, R, [0, 0, 20, 20]).solve(starts, goals)
+    z = np.zeros((N, 2))
+    n_cmp = 0
+    for b in range(B):
+        assert rs[b]["status"] == 0
+        dyn = scp_oracle.dynamics_residual(ts["accelerations"][b], starts[b], z, goals[b], z, h, [0, 0, 20, 20],
+                                           positions=ts["positions"][b])
+        assert dyn <= DYN_TOL, (b, dyn)
+        if rs[b]["qp_unsolved"] == 0 and rc[b]["qp_unsolved"] == 0 and rs[b]["scp_iterations"] == rc[b]["scp_iterations"]:
+            perr = np.linalg.norm(ts["positions"][b] - tc["positions"][b]) / np.linalg.norm(tc["positions"][b])
+            assert perr <= POS_TOL, (b, perr)
+            assert (rs[b]["min_separation"] >= R - 0.01) == (rc[b]["min_separation"] >= R - 0.01)
+            n_cmp += 1
+    assert n_cmp >= B // 3
+
+
+def test_stream_large_scenario_properties(torch_cuda):
+    """One 100-agent scenario (K=100, bounded-travel generator): dynamics feasible, separation holds, records consistent."""
+    from oracle import scp_oracle
+    from path_planning.scenarios.position_generator import generate_positions_large
+
+    random.seed(10_000)
+    N, T, h, R = 100, 20.0, 0.2, 0.8
+    p0, pf, space = generate_positions_large(N, R, time_horizon=T)
+    traj, recs, ms = _solve(p0, pf, T, h, R, space)
+    r = recs[0]
+    z = np.zeros((N, 2))
+    assert r["status"] == 0
+    dyn = scp_oracle.dynamics_residual(traj["accelerations"][0], p0, z, pf, z, h, space, positions=traj["positions"][0])
+    assert dyn <= DYN_TOL
+    assert abs(r["min_separation"] - scp_oracle.min_separation(traj["positions"][0])) <= 1e-12
+    if r["converged"] and r["qp_unsolved"] == 0:
+        assert r["min_separation"] >= R - 0.01
+    print(f"100 agents: {r['scp_iterations']} SCP iterations, {r['admm_iterations']} ADMM iterations, device {ms:.1f} ms, "
+          f"min separation {r['min_separation']:.4f}")
+
+
+def test_stream_agent_sharded_matches_single_gpu(torch_cuda):
+    """World-size-2 agent-sharded solve (NCCL all-gather of positions per ADMM iteration) == the one-GPU solve."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29631", os.path.join(ROOT, "tools", "run_sharded_scenario.py"), "--agents", "30", "--check"],
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SHARDED_CHECK_OK" in out.stdout
