@@ -174,8 +174,8 @@ int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents,
  *                with an NCCL all-gather of the positions (scp.py:463 is where the reference
  *                recomputes them), residual scalars are all-gathered at check iterations.
  * Subproblems end on the ADMM residual test (eps_abs/eps_rel of the problem), there is no polish.
- * n_steps <= 128.  Records use the fields of scp_b200_record (cycles_* and polish_* stay 0;
- * reserved2 bit 2 = the per-(step,agent) candidate capacity was exceeded). */
+ * n_steps <= 128.  The result records keep their meaning; cycles_* and polish_* stay 0 and
+ * reserved2 bit 2 says that the per-(step,agent) candidate capacity was exceeded. */
 typedef struct scp_b200_stream scp_b200_stream;
 
 /* 128-byte NCCL unique id (rank 0 creates it, the host side broadcasts it to the other ranks). */
