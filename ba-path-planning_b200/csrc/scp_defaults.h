@@ -25,7 +25,7 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->verify_tol = 1e-6;
   p->polish_first_eps = 5e-2;
   p->polish_first = 0;
-  p->reserved4 = 0;
+  p->relax_pct = 0;
   p->stall_window = 500;
   p->warm_duals = 0;
   p->polish_rounds = 40;

@@ -38,7 +38,7 @@ namespace ss {
 
 constexpr int NRED = 16;
 enum { R_PRI = 0, R_NPRI, R_DUA, R_NDUA, R_PRICOL, R_DN, R_PN, R_OBJ, R_MINSEP, R_FIRST, R_BAD, R_MAXD, R_COPIES, R_NCAND, R_OVER, R_SPARE };
-enum { FL_SCAN = 1, FL_GATE = 2, FL_VERIFY = 4, FL_SNAPSHOT = 8, FL_BUILD = 16, FL_KEEP = 32, FL_RESCALE = 64, FL_RESET = 128,
+enum { FL_SCAN = 1, FL_GATE = 2, FL_VERIFY = 4, FL_SNAPSHOT = 8, FL_BUILD = 16, FL_RESCALE = 64, FL_RESET = 128,
        FL_FACTOR = 256, FL_FINISH = 512 };
 constexpr int MAXC_MAX = 48;
 constexpr int AX_THREADS = 256;
@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
   const double h = d.pb.time_step, ih = 1.0 / h, rho = S.rho, sig = d.pb.sigma;
   const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
   const double cpr = (double)S.copies * rho;
+  // over-relaxation of the box rows (OSQP's alpha): v' = alpha A x' + (1 - alpha) z + (v - z)
+  const double alpha = (MODE <= 1 && d.pb.relax_pct > 0) ? 0.01 * (double)d.pb.relax_pct : 1.0;
   const double* N0 = d.N0 + (size_t)b * 2 * K;
   const double* Qm = d.Qm + (size_t)b * 2 * K;
   double trj[EPL], tra[EPL], trv[EPL], trp[EPL], trc[EPL];
@@ -277,12 +279,12 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
         if (k < K) {
           xo[e] = x[k];
           double v = va[k], z = clampd(v, -al, al);
-          sa[e] = v - z; wa[e] = tra[e] * (2 * z - v);
+          sa[e] = v - alpha * z; wa[e] = tra[e] * (2 * z - v);
           if (k < K - 1) {
-            v = vj[k]; z = clampd(v, -jl, jl); sj[e] = v - z; wj[e] = trj[e] * (2 * z - v);
-            v = vv[k]; z = clampd(v, lv, uv); sv[e] = v - z; wv[e] = trv[e] * (2 * z - v);
+            v = vj[k]; z = clampd(v, -jl, jl); sj[e] = v - alpha * z; wj[e] = trj[e] * (2 * z - v);
+            v = vv[k]; z = clampd(v, lv, uv); sv[e] = v - alpha * z; wv[e] = trv[e] * (2 * z - v);
             off[e] = p0q + h * (double)(k + 1) * v0q;
-            v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - z;
+            v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - alpha * z;
             wp[e] = trp[e] * (2 * z - v) + trc[e] * (P[k + 1] - off[e]) + F[k + 1];
           }
         }
@@ -368,13 +370,13 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
       first_next = __shfl_sync(0xffffffffu, xn[e], 0);
       if (k < K) {
         if (MODE <= 1) x[k] = xn[e];
-        const double nva = xn[e] + sa[e];
+        const double nva = alpha * xn[e] + sa[e];
         va[k] = nva;
         if (MODE == 1) { pr = fmax(pr, fabs(xn[e] - clampd(nva, -al, al))); nr = fmax(nr, fabs(xn[e])); }
         if (k < K - 1) {
           const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
           const double aj = (nxt - xn[e]) * ih;
-          const double nvj = aj + sj[e], nvv = rv_ + sv[e], nvp = rp_ + sp[e];
+          const double nvj = alpha * aj + sj[e], nvv = alpha * rv_ + sv[e], nvp = alpha * rp_ + sp[e];
           vj[k] = nvj; vv[k] = nvv; vp[k] = nvp;
           P[k + 1] = off[e] + rp_;
           if (MODE == 1) {
@@ -536,13 +538,13 @@ __device__ __forceinline__ void linearise_pair(double dx, double dy, int i, int 
   else { ex = dx / dist; ey = dy / dist; bound = R + ((ex * dx + ey * dy) - dist); }
 }
 
-// Candidate rows of (k, i): partners whose linearisation-point distance is below R + margin.  A rebuild (FL_KEEP,
-// after a verification failure enlarged the margin) keeps the multipliers of the rows already carried.
+// Candidate rows of (k, i): partners whose linearisation-point distance is below R + margin (multipliers start at
+// zero: OSQP starts every subproblem from y = 0, scp.py:441-443).  Rows that a later verification finds violated
+// are appended by k_scan.
 __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
   const int b = blockIdx.y;
   const State& S = d.st[b];
   if (!(S.flags & FL_BUILD)) return;
-  const int keep = S.flags & FL_KEEP;
   const int K = d.K, N = d.N, Nown = d.a_hi - d.a_lo;
   const int tl = blockIdx.x * blockDim.x + threadIdx.x;
   int mx = 0, over = 0;
@@ -550,10 +552,6 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
     const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
     if (k >= 1) {
       const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
-      int oj[MAXC_MAX];
-      double ol[MAXC_MAX];
-      int on = 0;
-      if (keep) { on = d.cnt[t]; for (int s = 0; s < on; ++s) { oj[s] = d.cj[(size_t)s * T + t]; ol[s] = d.lam[(size_t)s * T + t]; } }
       const double* Pb = d.Pbar + (size_t)b * d.Qs * K;
       const double pix = Pb[(size_t)(2 * i) * K + k], piy = Pb[(size_t)(2 * i + 1) * K + k];
       const double R = d.pb.min_distance, r2 = (R + S.margin) * (R + S.margin);
@@ -563,20 +561,17 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
         const double dx = pix - Pb[(size_t)(2 * j) * K + k], dy = piy - Pb[(size_t)(2 * j + 1) * K + k];
         if (dx * dx + dy * dy < r2) {
           if (n < d.maxc) {
-            double ex, ey, bound, l = 0.0;
+            double ex, ey, bound;
             linearise_pair(dx, dy, i, j, R, ex, ey, bound);
-            for (int s = 0; s < on; ++s) if (oj[s] == j) l = ol[s];
             const size_t o = (size_t)n * T + t;
-            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = l;
+            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0;
             ++n;
           } else over = 1;
         }
       }
       d.cnt[t] = n; mx = n;
-      if (!keep) {
-        const size_t r0 = ((size_t)b * d.Qs + 2 * i) * K + k;
-        d.F[r0] = 0.0; d.F[r0 + K] = 0.0; d.FY[r0] = 0.0; d.FY[r0 + K] = 0.0;
-      }
+      const size_t r0 = ((size_t)b * d.Qs + 2 * i) * K + k;
+      d.F[r0] = 0.0; d.F[r0 + K] = 0.0; d.FY[r0] = 0.0; d.FY[r0 + K] = 0.0;
     }
   }
   double nc = warp_sum((double)mx);
@@ -592,7 +587,8 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
 // ---------------------------------------------------------------------------------- pair scan
 // One thread per (scenario, own agent i, step k): all partners j.  Always: min separation of the current positions
 // (scp.py:597-615 quantity).  FL_GATE: first row (k-major, i<j) below R - margin.  FL_VERIFY: every row of the full
-// QP that is NOT carried is evaluated; violated rows are counted and the margin that would carry them is reduced.
+// QP that is NOT carried is evaluated; a violated one joins the candidate rows of (k, i) with multiplier 0 (its other
+// owner finds the same violation from the same numbers and appends its own copy), so the solve continues warm.
 __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
   const int b = blockIdx.y;
   const State& S = d.st[b];
@@ -600,9 +596,12 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
   const int gate = S.flags & FL_GATE, verify = S.flags & FL_VERIFY;
   const int K = d.K, N = d.N, Nown = d.a_hi - d.a_lo;
   const int tl = blockIdx.x * blockDim.x + threadIdx.x;
-  double mn = INFINITY, fr = INFINITY, bad = 0.0, maxd = 0.0;
+  double mn = INFINITY, fr = INFINITY, bad = 0.0, maxd = 0.0, over = 0.0;
   if (tl < Nown * K) {
     const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
+    const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
+    int n = (verify && k >= 1) ? d.cnt[t] : 0;
+    const int n0 = n;
     const double* Pc = d.P + (size_t)b * d.Qs * K;
     const double* Pb = d.Pbar + (size_t)b * d.Qs * K;
     const double px = Pc[(size_t)(2 * i) * K + k], py = Pc[(size_t)(2 * i + 1) * K + k];
@@ -624,10 +623,22 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
         if (!(d2 < r2)) {
           double ex, ey, bound;
           linearise_pair(dx, dy, i, j, R, ex, ey, bound);
-          if (ex * cx + ey * cy < bound - tol) { bad += 1.0; maxd = fmax(maxd, sqrt(d2)); }
+          if (ex * cx + ey * cy < bound - tol) {
+            int carried = 0;
+            for (int s = 0; s < n; ++s) carried |= (d.cj[(size_t)s * T + t] == j);
+            if (!carried) {
+              if (n < d.maxc) {
+                const size_t o = (size_t)n * T + t;
+                d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0;
+                ++n; bad += 1.0;
+              } else over = 1.0;
+            }
+          }
         }
       }
     }
+    if (n != n0) d.cnt[t] = n;
+    maxd = (double)n;                                 // largest candidate count after the appends
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
@@ -635,12 +646,15 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
     fr = fmin(fr, __shfl_xor_sync(0xffffffffu, fr, s));
     bad += __shfl_xor_sync(0xffffffffu, bad, s);
     maxd = fmax(maxd, __shfl_xor_sync(0xffffffffu, maxd, s));
+    over = fmax(over, __shfl_xor_sync(0xffffffffu, over, s));
   }
   if ((threadIdx.x & 31) == 0) {
     double* sl = d.slab + (size_t)b * NRED;
     if (mn < INFINITY) atomic_min_pos(sl + R_MINSEP, mn);
     if (fr < INFINITY) atomic_min_pos(sl + R_FIRST, fr);
-    if (bad > 0.0) { atomicAdd(sl + R_BAD, bad); atomic_max_pos(sl + R_MAXD, maxd); }
+    if (bad > 0.0) atomicAdd(sl + R_BAD, bad);        // rows appended (integer valued: exact in any order)
+    if (maxd > 0.0) atomic_max_pos(sl + R_MAXD, maxd);
+    if (over > 0.0) atomic_max_pos(sl + R_OVER, over);
   }
 }
 
@@ -784,10 +798,14 @@ __global__ void k_control2(const __grid_constant__ Dev d) {
     if (!finish) next_iter = 1;
   } else {
     if (S.qp_solved && (S.flags & FL_VERIFY) && bad > 0.0 && S.attempt < 20) {
+      // candidate rows were appended: same subproblem, warm state, operator rebuilt only if the copy count grew
       r.rebuilds++; S.attempt++;
-      const double need = (maxd - d.pb.min_distance) * (1.0 + 1e-9) + 1e-9;
-      S.margin = fmax(S.margin * (1.0 + 1e-9), need);
-      S.flags |= FL_BUILD | FL_KEEP;
+      const int copies = (int)maxd > S.copies ? (int)maxd : S.copies;
+      if (copies != S.copies) S.flags |= FL_FACTOR;
+      S.copies = copies; S.ncand += bad;
+      if (copies > r.max_copies) r.max_copies = copies;
+      if (combine(d, b, R_OVER, 0) > 0.0) r.reserved2 |= 4;
+      sl[R_OVER] = 0.0;
       start_qp(S, d);
     } else {
       if (!S.qp_solved) { r.qp_unsolved++; if (S.stalled) r.qp_infeasible++; }
@@ -873,6 +891,12 @@ struct scp_b200_stream {
   int* h_done = nullptr;          // pinned, 2 entries
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
   void* tables = nullptr;
+  cudaStream_t own = nullptr;     // the solver's stream (a captured graph cannot live on the legacy default stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_state = 0;            // 0: not tried, 1: one check period captured as a CUDA graph, -1: direct launches
+  double* in4 = nullptr;          // the solver's own copy of p0, v0, pf, vf (kernel arguments stay constant -> graph reuse)
+  scp_b200_record* rec_own = nullptr;
   void* io = nullptr;             // device staging of the host-buffer entry point
   size_t io_bytes = 0;
   int qpc = 8, nblk_q = 1, epl = 1;
@@ -948,7 +972,9 @@ void scp_b200_stream_destroy(scp_b200_stream* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->h_done) cudaFreeHost(s->h_done);
   if (s->io) cudaFree(s->io);
-  for (auto e : {s->ev[0], s->ev[1], s->t0, s->t1}) if (e) cudaEventDestroy(e);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  if (s->own) cudaStreamDestroy(s->own);
+  for (auto e : {s->ev[0], s->ev[1], s->t0, s->t1, s->ev_in, s->ev_out}) if (e) cudaEventDestroy(e);
   if (s->comm) { ss::NcclApi* api = ss::nccl_api(); if (api) api->CommDestroy(s->comm); }
   delete s;
 }
@@ -1010,6 +1036,12 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   if ((rc = dev_alloc(s, &d.acc, OUT))) return fail(rc);
   if ((rc = dev_alloc(s, &d.pos, OUT))) return fail(rc);
   if ((rc = dev_alloc(s, &d.vel, OUT))) return fail(rc);
+  if ((rc = dev_alloc(s, &s->in4, (size_t)4 * B * d.Q))) return fail(rc);
+  if ((rc = dev_alloc(s, &s->rec_own, (size_t)B))) return fail(rc);
+  d.p0 = s->in4; d.v0 = s->in4 + (size_t)B * d.Q; d.pf = s->in4 + 2 * (size_t)B * d.Q; d.vf = s->in4 + 3 * (size_t)B * d.Q;
+  d.rec = s->rec_own;
+  if (cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking) != cudaSuccess) return fail(scp_b200_set_error(100, "stream"));
+  for (cudaEvent_t* e : {&s->ev_in, &s->ev_out}) if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail(scp_b200_set_error(100, "event"));
   if (cudaMallocHost((void**)&s->h_done, 2 * sizeof(int)) != cudaSuccess) return fail(scp_b200_set_error(100, "pinned allocation failed"));
   for (cudaEvent_t* e : {&s->ev[0], &s->ev[1]}) if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail(scp_b200_set_error(100, "event"));
   for (cudaEvent_t* e : {&s->t0, &s->t1}) if (cudaEventCreate(e) != cudaSuccess) return fail(scp_b200_set_error(100, "event"));
@@ -1054,8 +1086,17 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   if (!s) return scp_b200_set_error(1, "null solver");
   ss::Dev& d = s->d;
   ss::NcclApi* api = ss::nccl_api();
-  cudaStream_t st = (cudaStream_t)stream;
-  d.p0 = d_p0; d.v0 = d_v0; d.pf = d_pf; d.vf = d_vf; d.rec = d_records;
+  cudaStream_t user = (cudaStream_t)stream, st = s->own;
+  // the solver works on its own stream, ordered after / before the caller's
+  SS_CUDA(cudaEventRecord(s->ev_in, user));
+  SS_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
+  {
+    const size_t n2 = (size_t)d.B * d.Q * sizeof(double);
+    SS_CUDA(cudaMemcpyAsync(s->in4, d_p0, n2, cudaMemcpyDeviceToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(s->in4 + (size_t)d.B * d.Q, d_v0, n2, cudaMemcpyDeviceToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(s->in4 + 2 * (size_t)d.B * d.Q, d_pf, n2, cudaMemcpyDeviceToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(s->in4 + 3 * (size_t)d.B * d.Q, d_vf, n2, cudaMemcpyDeviceToDevice, st));
+  }
   const int B = d.B, K = d.K, Nown = d.a_hi - d.a_lo, G = d.G;
   const dim3 g_elem((d.Qs * K + 255) / 256 < 64 ? (d.Qs * K + 255) / 256 : 64, B);
   const dim3 g_ik((Nown * K + 255) / 256 > 0 ? (Nown * K + 255) / 256 : 1, B);
@@ -1078,7 +1119,7 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   const long long max_macros = (long long)(d.pb.max_scp_iter + 2) * 22 * (d.pb.max_admm_iter / check + 2);
   s->h_done[0] = s->h_done[1] = 0;
   int rc = 0;
-  auto macro = [&](long long m) -> int {
+  auto body = [&]() -> int {
     for (int it = 1; it < check; ++it) {
       launch_axis<0>(s, st);
       if ((rc = gather_positions())) return rc;
@@ -1103,6 +1144,32 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
     ss::k_factor<<<B, 512, s->smem_factor, st>>>(d);
     ss::k_output<<<dim3((2 * Nown + 127) / 128 > 0 ? (2 * Nown + 127) / 128 : 1, B), 128, 0, st>>>(d);
     ss::k_finalize<<<g_b, 128, 0, st>>>(d);
+    return 0;
+  };
+  // one check period (check_every ADMM iterations + the control sequence) is captured once as a CUDA graph and
+  // replayed: ~90 launches per period cost one graph launch; SCP_B200_STREAM_GRAPH=0 keeps direct launches
+  if (s->graph_state == 0) {
+    const char* env = getenv("SCP_B200_STREAM_GRAPH");
+    s->graph_state = -1;
+    if (!(env && env[0] == '0')) {
+      if (G > 1) {   // NCCL sets up its connections on the first collective: keep that out of the capture
+        if ((rc = gather_positions())) return rc;
+        if ((rc = exchange())) return rc;
+      }
+      SS_CUDA(cudaStreamSynchronize(st));
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int brc = body();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (brc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&s->gexec, graph, 0) == cudaSuccess) s->graph_state = 1;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();
+    }
+  }
+  auto macro = [&](long long m) -> int {
+    if (s->graph_state == 1) SS_CUDA(cudaGraphLaunch(s->gexec, st));
+    else if ((rc = body())) return rc;
     SS_CUDA(cudaMemcpyAsync(&s->h_done[m & 1], d.done, sizeof(int), cudaMemcpyDeviceToHost, st));
     SS_CUDA(cudaEventRecord(s->ev[m & 1], st));
     return 0;
@@ -1133,7 +1200,10 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
     if (d_pos) SS_CUDA(cudaMemcpy2DAsync(d_pos, row, d.pos, prow, row, B, cudaMemcpyDeviceToDevice, st));
     if (d_vel) SS_CUDA(cudaMemcpy2DAsync(d_vel, row, d.vel, prow, row, B, cudaMemcpyDeviceToDevice, st));
   }
+  if (d_records) SS_CUDA(cudaMemcpyAsync(d_records, s->rec_own, (size_t)B * sizeof(scp_b200_record), cudaMemcpyDeviceToDevice, st));
   SS_CUDA(cudaEventRecord(s->t1, st));
+  SS_CUDA(cudaEventRecord(s->ev_out, st));
+  SS_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
   SS_CUDA(cudaStreamSynchronize(st));
   SS_CUDA(cudaGetLastError());
   if (device_ms) SS_CUDA(cudaEventElapsedTime(device_ms, s->t0, s->t1));

@@ -47,7 +47,7 @@ class Problem(C.Structure):
         ("verify_tol", C.c_double),
         ("polish_first_eps", C.c_double),
         ("polish_first", C.c_int32),
-        ("reserved4", C.c_int32),
+        ("relax_pct", C.c_int32),
         ("stall_window", C.c_int32),
         ("warm_duals", C.c_int32),
         ("polish_rounds", C.c_int32),

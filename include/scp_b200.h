@@ -59,7 +59,7 @@ typedef struct scp_b200_problem {
   double verify_tol;       /* dropped rows must hold to this tolerance */
   double polish_first_eps; /* residual gate: polish is tried once pri,dua <= gate*(1+norm) and the active set has settled */
   int32_t polish_first;    /* >0: polish attempt with this many rounds before the first ADMM iteration of a subproblem */
-  int32_t reserved4;
+  int32_t relax_pct;       /* streaming solver: ADMM over-relaxation alpha in percent (0 or 100: none; OSQP default 160) */
   int32_t stall_window;    /* give up on a subproblem whose primal residual stalls over this many iterations (0: off) */
   int32_t warm_duals;      /* 1: keep multipliers across SCP iterations (reference/OSQP restarts from y = 0) */
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */

@@ -108,3 +108,60 @@ def test_agent_blocks_balance_pair_rows():
     order = [(i, j) for i in range(n) for j in range(i + 1, n)]
     for p, (i, j) in enumerate(order):
         assert pair_index(i, n) + (j - i - 1) == p
+
+
+def test_stream_agent_block_partition():
+    """Equal blocks of ceil(N/world) agents (the per-iteration position all-gather needs equal slices); the tail
+    rank may own fewer, never a negative count; every agent is owned exactly once."""
+    from path_planning.solvers.stream import agent_block
+
+    for n in (1, 5, 30, 200, 1000, 1001):
+        for w in (1, 2, 3, 4, 8):
+            blocks = [agent_block(n, r, w) for r in range(w)]
+            per = -(-n // w)
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(lo <= hi and hi - lo <= per for lo, hi in blocks)
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(w - 1))
+            assert sum(hi - lo for lo, hi in blocks) == n
+
+
+def _id_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the plumbing StreamSolver uses to hand rank 0's 128-byte NCCL id to the other ranks
+    box = [bytes(range(128)) if rank == 0 else bytes(128)]
+    dist.broadcast_object_list(box, src=0)
+    from path_planning.solvers.stream import agent_block
+
+    q.put((rank, box[0] == bytes(range(128)), agent_block(30, rank, world)))
+    dist.destroy_process_group()
+
+
+def test_stream_id_broadcast_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_id_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, (0, 15)), (1, True, (15, 30))]
+
+
+def test_stream_solver_has_no_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from path_planning import _capi
+    from path_planning.solvers.stream import StreamSolver
+
+    with pytest.raises(_capi.ScpB200Error):
+        StreamSolver(5, 10.0, 0.2, 0.8)
