@@ -36,8 +36,9 @@ extern int scp_b200_set_error(int code, const char* msg);   // scp_b200.cu
 
 namespace ss {
 
-constexpr int NRED = 16;
-enum { R_PRI = 0, R_NPRI, R_DUA, R_NDUA, R_PRICOL, R_DN, R_PN, R_OBJ, R_MINSEP, R_FIRST, R_BAD, R_MAXD, R_COPIES, R_NCAND, R_OVER, R_SPARE };
+constexpr int NRED = 24;
+enum { R_PRI = 0, R_NPRI, R_DUA, R_NDUA, R_PRICOL, R_DN, R_PN, R_OBJ, R_MINSEP, R_FIRST, R_BAD, R_MAXD, R_COPIES, R_NCAND, R_OVER, R_SPARE,
+       R_VIOLJ, R_VIOLA, R_VIOLV, R_VIOLP };   // box-row classes outside the ADMM: max violation at the iterate
 enum { FL_SCAN = 1, FL_GATE = 2, FL_VERIFY = 4, FL_SNAPSHOT = 8, FL_BUILD = 16, FL_RESCALE = 64, FL_RESET = 128,
        FL_FACTOR = 256, FL_FINISH = 512 };
 constexpr int MAXC_MAX = 48;
@@ -47,6 +48,7 @@ struct State {
   int phase;        // 0: initial QP, 1: QP with collision rows, 2: finished
   int flags;        // work requested from the predicated kernels of this macro step
   int qp_it, scp_it, copies, attempt, have_state, qp_solved, stalled, it_mark;
+  int on_mask, pad_;   // box-row classes carried by the ADMM: 1 jerk, 2 acc, 4 vel, 8 pos
   double rho, est, margin, pri_mark, ncand;
   double pri, dua, dn, pn, obj, minsep;
 };
@@ -56,7 +58,8 @@ struct Dev {
   int B, N, K, Q, Qs;          // Qs = row stride of one scenario in the per-agent-axis arrays (>= Q, padded for the all-gather)
   int a_lo, a_hi;              // agents owned by this rank
   int maxc, G, rank;
-  const double *rj, *ra, *rv, *rp, *rc, *B1, *B2;
+  const double *rj, *ra, *rv, *rp, *rc, *B2;
+  const double* Bc[4];         // K x K unit-rho operators of the box-row classes: D'RjD, Ra, V'RvV, S'RpS
   double *x, *xprev, *va, *vj, *vv, *vp, *P, *Pbar, *F, *FY, *mu, *qsum;
   double *Nmat, *N0, *Qm, *gg;
   const double *p0, *v0, *pf, *vf;
@@ -140,7 +143,7 @@ __global__ void k_init(const __grid_constant__ Dev d) {
     if (threadIdx.x == 0) {
       State s;
       s.phase = 0; s.flags = FL_FACTOR; s.qp_it = 0; s.scp_it = 0; s.copies = 0; s.attempt = 0; s.have_state = 0; s.qp_solved = 0;
-      s.stalled = 0; s.it_mark = 0; s.rho = d.pb.rho0; s.est = 1.0; s.margin = d.pb.cand_margin; s.pri_mark = INFINITY; s.ncand = 0.0;
+      s.stalled = 0; s.it_mark = 0; s.on_mask = d.pb.lazy_rows ? 0 : 15; s.pad_ = 0; s.rho = d.pb.rho0; s.est = 1.0; s.margin = d.pb.cand_margin; s.pri_mark = INFINITY; s.ncand = 0.0;
       s.pri = s.dua = INFINITY; s.dn = s.pn = s.obj = 0.0; s.minsep = INFINITY;
       d.st[b] = s;
       scp_b200_record r;
@@ -169,9 +172,15 @@ __global__ void __launch_bounds__(512) k_factor(const __grid_constant__ Dev d) {
   double* mc = rowb + K;            // 2K
   __shared__ double G3[3];
   const double rho = S.rho, sig = d.pb.sigma, cp = (double)S.copies, h = d.pb.time_step;
+  const int on = S.on_mask;
   for (int e = tid; e < K * K; e += nt) {
     const int r = e / K, c = e - r * K;
-    M[e] = rho * (d.B1[e] + cp * d.B2[e]) + (r == c ? 2.0 + sig : 0.0);
+    double v = cp * d.B2[e];
+    if (on & 1) v += d.Bc[0][e];
+    if (on & 2) v += d.Bc[1][e];
+    if (on & 4) v += d.Bc[2][e];
+    if (on & 8) v += d.Bc[3][e];
+    M[e] = rho * v + (r == c ? 2.0 + sig : 0.0);
   }
   __syncthreads();
   for (int p = 0; p < K; ++p) {
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
   const double cpr = (double)S.copies * rho;
   // over-relaxation of the box rows (OSQP's alpha): v' = alpha A x' + (1 - alpha) z + (v - z)
   const double alpha = (MODE <= 1 && d.pb.relax_pct > 0) ? 0.01 * (double)d.pb.relax_pct : 1.0;
+  const int on = (MODE <= 1) ? S.on_mask : 0;
   const double* N0 = d.N0 + (size_t)b * 2 * K;
   const double* Qm = d.Qm + (size_t)b * 2 * K;
   double trj[EPL], tra[EPL], trv[EPL], trp[EPL], trc[EPL];
@@ -256,11 +266,13 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
   for (int e = 0; e < EPL; ++e) {
     const int k = lane + 32 * e;
     const bool in = k < K;
-    trj[e] = in ? rho * d.rj[k] : 0.0; tra[e] = in ? rho * d.ra[k] : 0.0;
-    trv[e] = in ? rho * d.rv[k] : 0.0; trp[e] = in ? rho * d.rp[k] : 0.0;
+    trj[e] = (in && (on & 1)) ? rho * d.rj[k] : 0.0; tra[e] = (in && (on & 2)) ? rho * d.ra[k] : 0.0;
+    trv[e] = (in && (on & 4)) ? rho * d.rv[k] : 0.0; trp[e] = (in && (on & 8)) ? rho * d.rp[k] : 0.0;
     trc[e] = in ? cpr * d.rc[k] : 0.0;
   }
-  double pr = 0.0, nr = 0.0;
+  // a class outside the ADMM keeps v = A x (no multiplier): s = 0 and no relaxation
+  const double alj = (on & 1) ? alpha : 1.0, ala = (on & 2) ? alpha : 1.0, alv = (on & 4) ? alpha : 1.0, alp = (on & 8) ? alpha : 1.0;
+  double pr = 0.0, nr = 0.0, voj = 0.0, voa = 0.0, vov = 0.0, vop = 0.0;
   for (int q = qa + warp; q < qb; q += nw) {
     const size_t row = ((size_t)b * d.Qs + q) * K;
     const size_t q2 = (size_t)b * d.Q + q;
@@ -279,12 +291,12 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
         if (k < K) {
           xo[e] = x[k];
           double v = va[k], z = clampd(v, -al, al);
-          sa[e] = v - alpha * z; wa[e] = tra[e] * (2 * z - v);
+          sa[e] = (on & 2) ? v - alpha * z : 0.0; wa[e] = tra[e] * (2 * z - v);
           if (k < K - 1) {
-            v = vj[k]; z = clampd(v, -jl, jl); sj[e] = v - alpha * z; wj[e] = trj[e] * (2 * z - v);
-            v = vv[k]; z = clampd(v, lv, uv); sv[e] = v - alpha * z; wv[e] = trv[e] * (2 * z - v);
+            v = vj[k]; z = clampd(v, -jl, jl); sj[e] = (on & 1) ? v - alpha * z : 0.0; wj[e] = trj[e] * (2 * z - v);
+            v = vv[k]; z = clampd(v, lv, uv); sv[e] = (on & 4) ? v - alpha * z : 0.0; wv[e] = trv[e] * (2 * z - v);
             off[e] = p0q + h * (double)(k + 1) * v0q;
-            v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - alpha * z;
+            v = vp[k]; z = clampd(v, plo - off[e], phi - off[e]); sp[e] = (on & 8) ? v - alpha * z : 0.0;
             wp[e] = trp[e] * (2 * z - v) + trc[e] * (P[k + 1] - off[e]) + F[k + 1];
           }
         }
@@ -370,19 +382,25 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
       first_next = __shfl_sync(0xffffffffu, xn[e], 0);
       if (k < K) {
         if (MODE <= 1) x[k] = xn[e];
-        const double nva = alpha * xn[e] + sa[e];
+        const double nva = ala * xn[e] + sa[e];
         va[k] = nva;
-        if (MODE == 1) { pr = fmax(pr, fabs(xn[e] - clampd(nva, -al, al))); nr = fmax(nr, fabs(xn[e])); }
+        if (MODE == 1) {
+          const double dv = fabs(xn[e] - clampd(nva, -al, al));
+          if (on & 2) pr = fmax(pr, dv); else voa = fmax(voa, dv);
+          nr = fmax(nr, fabs(xn[e]));
+        }
         if (k < K - 1) {
           const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
           const double aj = (nxt - xn[e]) * ih;
-          const double nvj = alpha * aj + sj[e], nvv = alpha * rv_ + sv[e], nvp = alpha * rp_ + sp[e];
+          const double nvj = alj * aj + sj[e], nvv = alv * rv_ + sv[e], nvp = alp * rp_ + sp[e];
           vj[k] = nvj; vv[k] = nvv; vp[k] = nvp;
           P[k + 1] = off[e] + rp_;
           if (MODE == 1) {
-            pr = fmax(pr, fabs(aj - clampd(nvj, -jl, jl)));
-            pr = fmax(pr, fabs(rv_ - clampd(nvv, lv, uv)));
-            pr = fmax(pr, fabs(rp_ - clampd(nvp, plo - off[e], phi - off[e])));
+            const double dj = fabs(aj - clampd(nvj, -jl, jl)), dv = fabs(rv_ - clampd(nvv, lv, uv));
+            const double dp = fabs(rp_ - clampd(nvp, plo - off[e], phi - off[e]));
+            if (on & 1) pr = fmax(pr, dj); else voj = fmax(voj, dj);
+            if (on & 4) pr = fmax(pr, dv); else vov = fmax(vov, dv);
+            if (on & 8) pr = fmax(pr, dp); else vop = fmax(vop, dp);
             nr = fmax(nr, fmax(fabs(aj), fmax(fabs(rv_), fabs(rp_))));
           }
         }
@@ -392,6 +410,16 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
   if (MODE == 1) {
     pr = warp_max_nan(fabs(pr)); nr = warp_max_nan(fabs(nr));
     if (lane == 0) { atomic_max_pos(d.slab + (size_t)b * NRED + R_PRI, pr); atomic_max_pos(d.slab + (size_t)b * NRED + R_NPRI, nr); }
+    if (on != 15) {
+      voj = warp_max(voj); voa = warp_max(voa); vov = warp_max(vov); vop = warp_max(vop);
+      if (lane == 0) {
+        double* sl = d.slab + (size_t)b * NRED;
+        if (voj > 0.0) atomic_max_pos(sl + R_VIOLJ, voj);
+        if (voa > 0.0) atomic_max_pos(sl + R_VIOLA, voa);
+        if (vov > 0.0) atomic_max_pos(sl + R_VIOLV, vov);
+        if (vop > 0.0) atomic_max_pos(sl + R_VIOLP, vop);
+      }
+    }
   }
 }
 
@@ -413,6 +441,7 @@ __global__ void __launch_bounds__(AX_THREADS) k_dual(const __grid_constant__ Dev
   const double v0q = d.v0[q2], p0q = d.p0[q2];
   const double lv = -vl - v0q, uv = vl - v0q;
   const double plo = d.pb.space[q & 1], phi = d.pb.space[2 + (q & 1)];
+  const int on = S.on_mask;
   const double *x = d.x + row, *xp = d.xprev + row, *vj = d.vj + row, *va = d.va + row, *vv = d.vv + row, *vp = d.vp + row, *FY = d.FY + row;
   double xo[EPL], wj[EPL], wa[EPL], r1v[EPL], r1p[EPL], r2p[EPL];
   double dn = 0.0, pn = 0.0, ob = 0.0;
@@ -425,12 +454,12 @@ __global__ void __launch_bounds__(AX_THREADS) k_dual(const __grid_constant__ Dev
       const double xq = xp[k];
       dn += (xo[e] - xq) * (xo[e] - xq); pn += xq * xq; ob += xo[e] * xo[e];
       double v = va[k], z = clampd(v, -al, al);
-      wa[e] = rho * d.ra[k] * (v - z);
+      wa[e] = (on & 2) ? rho * d.ra[k] * (v - z) : 0.0;
       if (k < K - 1) {
-        v = vj[k]; z = clampd(v, -jl, jl); wj[e] = rho * d.rj[k] * (v - z);
-        v = vv[k]; z = clampd(v, lv, uv); r1v[e] = rho * d.rv[k] * (v - z);
+        v = vj[k]; z = clampd(v, -jl, jl); wj[e] = (on & 1) ? rho * d.rj[k] * (v - z) : 0.0;
+        v = vv[k]; z = clampd(v, lv, uv); r1v[e] = (on & 4) ? rho * d.rv[k] * (v - z) : 0.0;
         const double off = p0q + h * (double)(k + 1) * v0q;
-        v = vp[k]; z = clampd(v, plo - off, phi - off); r1p[e] = rho * d.rp[k] * (v - z) - FY[k + 1];
+        v = vp[k]; z = clampd(v, plo - off, phi - off); r1p[e] = ((on & 8) ? rho * d.rp[k] * (v - z) : 0.0) - FY[k + 1];
       }
     }
   }
@@ -670,13 +699,14 @@ __global__ void k_rescale(const __grid_constant__ Dev d) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nq * K; e += gridDim.x * blockDim.x) {
     const int ql = e / K, k = e - ql * K, q = 2 * d.a_lo + ql;
     const size_t o = ((size_t)b * d.Qs + q) * K + k;
-    double v = d.va[o], z = clampd(v, -al, al); d.va[o] = z + (v - z) / est;
+    const int on = S.on_mask;
+    double v = d.va[o], z = clampd(v, -al, al); if (on & 2) d.va[o] = z + (v - z) / est;
     if (k < K - 1) {
       const double v0q = d.v0[(size_t)b * d.Q + q], p0q = d.p0[(size_t)b * d.Q + q];
       const double off = p0q + h * (double)(k + 1) * v0q;
-      v = d.vj[o]; z = clampd(v, -jl, jl); d.vj[o] = z + (v - z) / est;
-      v = d.vv[o]; z = clampd(v, -vl - v0q, vl - v0q); d.vv[o] = z + (v - z) / est;
-      v = d.vp[o]; z = clampd(v, d.pb.space[q & 1] - off, d.pb.space[2 + (q & 1)] - off); d.vp[o] = z + (v - z) / est;
+      v = d.vj[o]; z = clampd(v, -jl, jl); if (on & 1) d.vj[o] = z + (v - z) / est;
+      v = d.vv[o]; z = clampd(v, -vl - v0q, vl - v0q); if (on & 4) d.vv[o] = z + (v - z) / est;
+      v = d.vp[o]; z = clampd(v, d.pb.space[q & 1] - off, d.pb.space[2 + (q & 1)] - off); if (on & 8) d.vp[o] = z + (v - z) / est;
     }
   }
 }
@@ -730,8 +760,11 @@ __global__ void k_control1(const __grid_constant__ Dev d) {
   if (!(pc <= pri)) pri = pc;
   const double npri = combine(d, b, R_NPRI, 0), dua = combine(d, b, R_DUA, 0), ndua = combine(d, b, R_NDUA, 0);
   S.dn = combine(d, b, R_DN, 1); S.pn = combine(d, b, R_PN, 1); S.obj = combine(d, b, R_OBJ, 1);
+  double viol[4];
+  for (int c = 0; c < 4; ++c) viol[c] = combine(d, b, R_VIOLJ + c, 0);
   double* sl = d.slab + (size_t)b * NRED;
   for (int s = 0; s <= R_OBJ; ++s) sl[s] = 0.0;
+  for (int c = 0; c < 4; ++c) sl[R_VIOLJ + c] = 0.0;
   const int check = d.pb.check_every, maxit = d.pb.max_admm_iter;
   S.qp_it += check;
   scp_b200_record& r = d.rec[b];
@@ -740,7 +773,18 @@ __global__ void k_control1(const __grid_constant__ Dev d) {
   S.pri = pri; S.dua = dua;
   const double ea = d.pb.eps_abs, er = d.pb.eps_rel;
   const int nan = !(pri == pri) || !(dua == dua);
-  const int solved = !nan && pri <= ea + er * npri && dua <= ea + er * ndua;
+  int solved = !nan && pri <= ea + er * npri && dua <= ea + er * ndua;
+  if (solved && S.on_mask != 15) {
+    // the iterate solves the QP without the box-row classes that are outside the ADMM: a violated class joins
+    // (its v already equals A x, i.e. multiplier 0) and the same subproblem continues warm
+    int add = 0;
+    for (int c = 0; c < 4; ++c) if (!(S.on_mask & (1 << c)) && viol[c] > ea + er * npri) add |= 1 << c;
+    if (add) {
+      S.on_mask |= add; S.flags |= FL_FACTOR; solved = 0;
+      S.it_mark = S.qp_it; S.pri_mark = INFINITY;
+      r.rebuilds++;
+    }
+  }
   int stalled = 0;
   if (!solved && !nan && d.pb.stall_window > 0 && S.qp_it - S.it_mark >= d.pb.stall_window) {
     if (pri > 1e-3 * (1.0 + npri) && pri > 0.8 * S.pri_mark) stalled = 1;
@@ -1007,12 +1051,26 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   const int Nown = d.a_hi - d.a_lo;
   int rc = 0;
   auto fail = [&](int code) { scp_b200_stream_destroy(s); return code; };
-  // tables
-  scp::HostTables t = scp::build_host_tables(d.pb);
-  double* tb = nullptr;
-  if ((rc = dev_alloc(s, &tb, t.blob.size()))) return fail(rc);
-  if (cudaMemcpy(tb, t.blob.data(), t.blob.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail(scp_b200_set_error(100, "table upload failed"));
-  d.B1 = tb; d.B2 = tb + (size_t)K * K; d.rj = tb + 2 * (size_t)K * K; d.ra = d.rj + K; d.rv = d.ra + K; d.rp = d.rv + K; d.rc = d.rp + K;
+  // tables: row weights and S'RcS as in scp_tables.h; the box-row operator is kept per class (it is linear in the
+  // class weights) so that a scenario's operator can be assembled from the classes its ADMM carries
+  {
+    scp::HostTables t = scp::build_host_tables(d.pb);
+    std::vector<double> blob(t.blob.begin() + (size_t)K * K, t.blob.end());          // [B2 | rj ra rv rp rc]
+    for (int c = 0; c < 4; ++c) {
+      scp_b200_problem pc = d.pb;
+      if (c != 0) pc.w_jerk = 0.0;
+      if (c != 1) pc.w_acc = 0.0;
+      if (c != 2) pc.w_vel = 0.0;
+      if (c != 3) pc.w_pos = 0.0;
+      scp::HostTables tc = scp::build_host_tables(pc);
+      blob.insert(blob.end(), tc.blob.begin(), tc.blob.begin() + (size_t)K * K);
+    }
+    double* tb = nullptr;
+    if ((rc = dev_alloc(s, &tb, blob.size()))) return fail(rc);
+    if (cudaMemcpy(tb, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return fail(scp_b200_set_error(100, "table upload failed"));
+    d.B2 = tb; d.rj = tb + (size_t)K * K; d.ra = d.rj + K; d.rv = d.ra + K; d.rp = d.rv + K; d.rc = d.rp + K;
+    for (int c = 0; c < 4; ++c) d.Bc[c] = d.rc + K + (size_t)c * K * K;
+  }
   const size_t QK = (size_t)B * d.Qs * K;
   double** arrs[] = {&d.x, &d.xprev, &d.va, &d.vj, &d.vv, &d.vp, &d.P, &d.Pbar, &d.F, &d.FY};
   for (double** a : arrs) if ((rc = dev_alloc(s, a, QK))) return fail(rc);

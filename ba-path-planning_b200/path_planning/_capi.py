@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 MAX_SCP_ITER = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libscp_b200.so")
@@ -52,6 +52,8 @@ class Problem(C.Structure):
         ("warm_duals", C.c_int32),
         ("polish_rounds", C.c_int32),
         ("team_mode", C.c_int32),
+        ("lazy_rows", C.c_int32),
+        ("reserved5", C.c_int32),
     ]
 
 

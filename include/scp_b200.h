@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCP_B200_ABI_VERSION 1
+#define SCP_B200_ABI_VERSION 2
 #define SCP_B200_MAX_SCP_ITER 32
 
 /* Problem definition shared by every scenario of a batch.
@@ -64,6 +64,10 @@ typedef struct scp_b200_problem {
   int32_t warm_duals;      /* 1: keep multipliers across SCP iterations (reference/OSQP restarts from y = 0) */
   int32_t polish_rounds;   /* add/drop rounds per polish attempt */
   int32_t team_mode;       /* 0 auto, 1 one CTA per scenario, 2 whole cooperative grid per scenario */
+  int32_t lazy_rows;       /* streaming solver: 1 = the box-row classes (jerk, acc, vel, pos) start outside the ADMM and a
+                              class joins, per scenario, when a converged iterate violates it (verify-and-enlarge, as
+                              for the collision rows); 0 = all box rows carried from the start */
+  int32_t reserved5;
 } scp_b200_problem;
 
 /* Per-scenario result record (device or host array of B records). */
