@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../../include/scp_b200.h"
+#include "scp_defaults.h"
 #include "scp_tables.h"
 
 extern int scp_b200_set_error(int code, const char* msg);   // scp_b200.cu
@@ -1001,6 +1002,19 @@ void set_axis_smem(F f, size_t smem) { cudaFuncSetAttribute(f, cudaFuncAttribute
 }  // namespace
 
 extern "C" {
+
+// Defaults of the streaming solver: the reference's problem data (scp.py:32-74) with the ADMM settings that suit a
+// solve without polish (fixed rho, OSQP's over-relaxation 1.6, residual tolerance 1e-4, a larger iteration cap).
+void scp_b200_stream_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon, double time_step,
+                                     double min_distance) {
+  scp_fill_default_problem(prob, n_agents, time_horizon, time_step, min_distance);
+  prob->polish = 0;
+  prob->adapt_every = 0;
+  prob->relax_pct = 160;
+  prob->eps_abs = 1e-4; prob->eps_rel = 1e-4;
+  prob->max_admm_iter = 20000;
+  prob->lazy_rows = 1;
+}
 
 int scp_b200_nccl_unique_id(void* id128) {
   ss::NcclApi* api = ss::nccl_api();

@@ -126,6 +126,7 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "scp_b200_stream_default_problem": (None, [_P(Problem), C.c_int, C.c_double, C.c_double, C.c_double]),
     "scp_b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "scp_b200_stream_create": (
         C.c_int, [_P(Problem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_void_p)]),
@@ -187,9 +188,10 @@ def check(rc):
         raise ScpB200Error(f"scp_b200 error {rc}: {msg.decode() if msg else '?'}")
 
 
-def default_problem(n_agents, time_horizon, time_step, min_distance, space_dims=None, lib=None) -> Problem:
+def default_problem(n_agents, time_horizon, time_step, min_distance, space_dims=None, lib=None, stream=False) -> Problem:
     p = Problem()
-    (lib or load()).scp_b200_default_problem(C.byref(p), int(n_agents), float(time_horizon), float(time_step),
+    fn = (lib or load()).scp_b200_stream_default_problem if stream else (lib or load()).scp_b200_default_problem
+    fn(C.byref(p), int(n_agents), float(time_horizon), float(time_step),
                                              float(min_distance))
     if space_dims is not None:
         for i in range(4):

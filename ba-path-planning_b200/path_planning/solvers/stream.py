@@ -34,7 +34,7 @@ class StreamSolver:
         torch = _require_cuda()
         self.torch = torch
         self.lib = _capi.load()
-        self.problem = _capi.default_problem(n_vehicles, time_horizon, time_step, min_distance, space_dims)
+        self.problem = _capi.default_problem(n_vehicles, time_horizon, time_step, min_distance, space_dims, stream=True)
         for k, v in settings.items():
             if not hasattr(self.problem, k):
                 raise TypeError(f"unknown solver setting {k!r}")

@@ -182,6 +182,11 @@ int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents,
  * reserved2 bit 2 says that the per-(step,agent) candidate capacity was exceeded. */
 typedef struct scp_b200_stream scp_b200_stream;
 
+/* scp_b200_default_problem with the ADMM settings that suit the streaming solver (fixed rho, over-relaxation 1.6,
+ * eps 1e-4, iteration cap 20000, lazy box rows). */
+void scp_b200_stream_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon,
+                                     double time_step, double min_distance);
+
 /* 128-byte NCCL unique id (rank 0 creates it, the host side broadcasts it to the other ranks). */
 int scp_b200_nccl_unique_id(void* id128);
 
