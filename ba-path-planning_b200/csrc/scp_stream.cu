@@ -19,6 +19,7 @@
 //   k_control*      termination + SCP loop            generate_trajectories                :152-166
 //   k_output        result dict                       :168-175
 
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only: every NCCL function is resolved with dlsym at run time
@@ -49,7 +50,7 @@ struct State {
   int phase;        // 0: initial QP, 1: QP with collision rows, 2: finished
   int flags;        // work requested from the predicated kernels of this macro step
   int qp_it, scp_it, copies, attempt, have_state, qp_solved, stalled, it_mark;
-  int on_mask, pad_;   // box-row classes carried by the ADMM: 1 jerk, 2 acc, 4 vel, 8 pos
+  int on_mask, reset_mask;   // box-row classes carried by the ADMM (1 jerk, 2 acc, 4 vel, 8 pos); classes whose v := A x on FL_RESET
   double rho, est, margin, pri_mark, ncand;
   double pri, dua, dn, pn, obj, minsep;
 };
@@ -61,11 +62,11 @@ struct Dev {
   int maxc, G, rank;
   const double *rj, *ra, *rv, *rp, *rc, *B2;
   const double* Bc[4];         // K x K unit-rho operators of the box-row classes: D'RjD, Ra, V'RvV, S'RpS
-  double *x, *xprev, *va, *vj, *vv, *vp, *P, *Pbar, *F, *FY, *mu, *qsum;
+  double *x, *xprev, *va, *vj, *vv, *vp, *P, *P1, *Pbar, *F, *FY, *mu, *qsum;   // P / P1: position ping-pong (P is current between check periods)
   double *Nmat, *N0, *Qm, *gg;
   const double *p0, *v0, *pf, *vf;
   int *cnt, *cj;
-  double *cex, *cey, *cb, *lam;
+  double *cex, *cey, *cb, *lam, *lam1;   // lam / lam1: multiplier ping-pong (lam is current between check periods)
   double *slab, *gath;
   State* st;
   scp_b200_record* rec;
@@ -133,7 +134,7 @@ __global__ void k_init(const __grid_constant__ Dev d) {
     double p = 0.0;
     if (q < d.Q) { const double p0 = d.p0[(size_t)b * d.Q + q], v0 = d.v0[(size_t)b * d.Q + q]; p = p0 + h * (double)k * v0; }
     d.x[base + e] = 0.0; d.xprev[base + e] = 0.0; d.va[base + e] = 0.0; d.vj[base + e] = 0.0; d.vv[base + e] = 0.0; d.vp[base + e] = 0.0;
-    d.P[base + e] = p; d.Pbar[base + e] = p; d.F[base + e] = 0.0; d.FY[base + e] = 0.0;
+    d.P[base + e] = p; d.P1[base + e] = p; d.Pbar[base + e] = p; d.F[base + e] = 0.0; d.FY[base + e] = 0.0;
   }
   const int Nown = d.a_hi - d.a_lo;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Nown * K; t += gridDim.x * blockDim.x) d.cnt[(size_t)b * Nown * K + t] = 0;
@@ -144,7 +145,7 @@ __global__ void k_init(const __grid_constant__ Dev d) {
     if (threadIdx.x == 0) {
       State s;
       s.phase = 0; s.flags = FL_FACTOR; s.qp_it = 0; s.scp_it = 0; s.copies = 0; s.attempt = 0; s.have_state = 0; s.qp_solved = 0;
-      s.stalled = 0; s.it_mark = 0; s.on_mask = d.pb.lazy_rows ? 0 : 15; s.pad_ = 0; s.rho = d.pb.rho0; s.est = 1.0; s.margin = d.pb.cand_margin; s.pri_mark = INFINITY; s.ncand = 0.0;
+      s.stalled = 0; s.it_mark = 0; s.on_mask = d.pb.lazy_rows ? 0 : 15; s.reset_mask = 0; s.rho = d.pb.rho0; s.est = 1.0; s.margin = d.pb.cand_margin; s.pri_mark = INFINITY; s.ncand = 0.0;
       s.pri = s.dua = INFINITY; s.dn = s.pn = s.obj = 0.0; s.minsep = INFINITY;
       d.st[b] = s;
       scp_b200_record r;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
       if (k < K) {
         if (MODE <= 1) x[k] = xn[e];
         const double nva = ala * xn[e] + sa[e];
-        va[k] = nva;
+        if (MODE <= 1 || (S.reset_mask & 2)) va[k] = nva;
         if (MODE == 1) {
           const double dv = fabs(xn[e] - clampd(nva, -al, al));
           if (on & 2) pr = fmax(pr, dv); else voa = fmax(voa, dv);
@@ -394,8 +395,10 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
           const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
           const double aj = (nxt - xn[e]) * ih;
           const double nvj = alj * aj + sj[e], nvv = alv * rv_ + sv[e], nvp = alp * rp_ + sp[e];
-          vj[k] = nvj; vv[k] = nvv; vp[k] = nvp;
-          P[k + 1] = off[e] + rp_;
+          if (MODE <= 1 || (S.reset_mask & 1)) vj[k] = nvj;
+          if (MODE <= 1 || (S.reset_mask & 4)) vv[k] = nvv;
+          if (MODE <= 1 || (S.reset_mask & 8)) vp[k] = nvp;
+          if (MODE <= 1) P[k + 1] = off[e] + rp_;
           if (MODE == 1) {
             const double dj = fabs(aj - clampd(nvj, -jl, jl)), dv = fabs(rv_ - clampd(nvv, lv, uv));
             const double dp = fabs(rp_ - clampd(nvp, plo - off[e], phi - off[e]));
@@ -422,6 +425,361 @@ __global__ void __launch_bounds__(AX_THREADS) k_axis(const __grid_constant__ Dev
       }
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------- fused ADMM iteration
+// ONE kernel per ADMM iteration.  One warp per (scenario, agent); lane L owns the EPL consecutive steps
+// k = L*EPL .. L*EPL+EPL-1 ("blocked": a scan over k is EPL local adds + ONE warp scan, rows move as 16-byte vectors).
+//   1. collision rows of the agent at its steps (candidate walk, multiplier update, force on p_i[k]) from the
+//      positions of the PREVIOUS iterate (buffer `cur`) -- both owners of a row see the same numbers, so their
+//      copies of the multiplier stay identical (scp_device.inl collision_rows);
+//   2. for each axis: box rows -> right-hand side (transposed scans), x = Nmat rhs + N0 d with the K x K operator
+//      staged in shared memory by cp.async while step 1 runs, forward scans -> rows of A x, new positions into
+//      buffer `cur ^ 1` (scp_device.inl admm_iter_fused).
+// Box-row classes outside the ADMM (lazy rows) cost no memory traffic: only their violation is reduced at checks.
+// CHK = 1 adds the primal residual terms, the equality multipliers and sum_j lam eta (FY) for the dual residual.
+constexpr int IT_THREADS = 256;   // 8 warps = 4 agents x 2 axes
+
+template <int EPL>
+__device__ __forceinline__ void load_row(const double* __restrict__ p, int k0, int K, bool vec, double (&v)[EPL]) {
+  if ((EPL & 1) == 0 && vec) {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) {
+      double2 t = make_double2(0.0, 0.0);
+      if (k0 + e < K) t = *reinterpret_cast<const double2*>(p + k0 + e);
+      v[e] = t.x; v[e + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) v[e] = (k0 + e < K) ? p[k0 + e] : 0.0;
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void store_row(double* __restrict__ p, int k0, int K, bool vec, const double (&v)[EPL]) {
+  if ((EPL & 1) == 0 && vec) {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2)
+      if (k0 + e < K) *reinterpret_cast<double2*>(p + k0 + e) = make_double2(v[e], v[e + 1]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) if (k0 + e < K) p[k0 + e] = v[e];
+  }
+}
+
+// inclusive suffix sums over k of a (first order) and of (b, then once more: c = suffix of suffix of b)
+template <int EPL>
+__device__ __forceinline__ void suffix3(double (&a)[EPL], double (&b)[EPL], double (&c)[EPL], int lane) {
+  double ta = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+  for (int e = EPL - 1; e >= 0; --e) { ta += a[e]; a[e] = ta; t1 += b[e]; b[e] = t1; t2 += t1; c[e] = t2; }
+  double ia = ta, i1 = t1, i2 = t2;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const double oa = __shfl_down_sync(0xffffffffu, ia, dd), o1 = __shfl_down_sync(0xffffffffu, i1, dd), o2 = __shfl_down_sync(0xffffffffu, i2, dd);
+    if (lane + dd < 32) { ia += oa; i2 += o2 + (double)(dd * EPL) * o1; i1 += o1; }
+  }
+  double ca = __shfl_down_sync(0xffffffffu, ia, 1), c1 = __shfl_down_sync(0xffffffffu, i1, 1), c2 = __shfl_down_sync(0xffffffffu, i2, 1);
+  if (lane == 31) { ca = 0.0; c1 = 0.0; c2 = 0.0; }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { a[e] += ca; c[e] += c2 + (double)(EPL - e) * c1; b[e] += c1; }
+}
+// inclusive prefix sums: b = prefix of a's values given in b, c = prefix of prefix
+template <int EPL>
+__device__ __forceinline__ void prefix2(double (&b)[EPL], double (&c)[EPL], int lane) {
+  double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { t1 += b[e]; b[e] = t1; t2 += t1; c[e] = t2; }
+  double i1 = t1, i2 = t2;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const double o1 = __shfl_up_sync(0xffffffffu, i1, dd), o2 = __shfl_up_sync(0xffffffffu, i2, dd);
+    if (lane >= dd) { i2 += o2 + (double)(dd * EPL) * o1; i1 += o1; }
+  }
+  double c1 = __shfl_up_sync(0xffffffffu, i1, 1), c2 = __shfl_up_sync(0xffffffffu, i2, 1);
+  if (lane == 0) { c1 = 0.0; c2 = 0.0; }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { c[e] += c2 + (double)(e + 1) * c1; b[e] += c1; }
+}
+
+// BOX = 0: no box-row class is carried by this scenario's ADMM (the usual state with lazy rows) -- all box code
+// compiles away and only x and the positions move through memory.
+template <int EPL, int CHK, int BOX>
+__device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc, int cur, double* sm) {
+  const int b = blockIdx.y;
+  const int K = d.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, npair = blockDim.x >> 6;
+  const int ia = d.a_lo + blockIdx.x * apc, ib = min(ia + apc, d.a_hi);
+  const int ax = warp & 1;                                    // two warps per agent: one per axis
+  double* Nm = sm;
+  double* myrhs = sm + (size_t)K * K + (size_t)warp * (K + (K & 1));
+  const bool vec = (K & 1) == 0;
+  {  // operator -> shared memory, asynchronously (cp.async 16 B) when rows are 16-byte aligned
+    const double* src = d.Nmat + (size_t)b * K * K;
+    if (vec) {
+      for (int e = threadIdx.x; e < K * K / 2; e += blockDim.x) __pipeline_memcpy_async(Nm + 2 * e, src + 2 * e, 16);
+      __pipeline_commit();
+    } else {
+      for (int e = threadIdx.x; e < K * K; e += blockDim.x) Nm[e] = src[e];
+    }
+  }
+  const double h = d.pb.time_step, ih = 1.0 / h, rho = S.rho, sig = d.pb.sigma;
+  const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
+  const double cpr = (double)S.copies * rho;
+  const double alpha = d.pb.relax_pct > 0 ? 0.01 * (double)d.pb.relax_pct : 1.0;
+  const int on = BOX ? S.on_mask : 0;
+  const double* N0 = d.N0 + (size_t)b * 2 * K;
+  const double* Qm = d.Qm + (size_t)b * 2 * K;
+  const double* Pc = (cur ? d.P1 : d.P) + (size_t)b * d.Qs * K;
+  double* Pn = (cur ? d.P : d.P1) + (size_t)b * d.Qs * K;
+  const double* lamc = cur ? d.lam1 : d.lam;
+  double* lamn = cur ? d.lam : d.lam1;
+  const int k0 = lane * EPL;
+  const int Nown = d.a_hi - d.a_lo;
+  const size_t T = (size_t)d.B * Nown * K;
+  double trj[EPL], tra[EPL], trv[EPL], trp[EPL], trc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int k = k0 + e;
+    const bool in = k < K;
+    trj[e] = (in && (on & 1)) ? rho * d.rj[k] : 0.0; tra[e] = (in && (on & 2)) ? rho * d.ra[k] : 0.0;
+    trv[e] = (in && (on & 4)) ? rho * d.rv[k] : 0.0; trp[e] = (in && (on & 8)) ? rho * d.rp[k] : 0.0;
+    trc[e] = in ? cpr * d.rc[k] : 0.0;
+  }
+  double pr = 0.0, nr = 0.0, voj = 0.0, voa = 0.0, vov = 0.0, vop = 0.0, worst = 0.0;
+  bool staged = false;
+  for (int i = ia + (warp >> 1); i < ib || !staged; i += npair) {
+    const bool live = i < ib;      // every warp passes the staging barrier once, even without an agent of its own
+    // ---- 1. collision rows of agent i: this axis' component of the force on state k (fz[e] <-> state k0+e).
+    // Both axis warps walk the rows and compute the same multipliers; the x warp stores them (other buffer).
+    double fz[EPL], fyo[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { fz[e] = 0.0; fyo[e] = 0.0; }
+    if (live && S.phase == 1) {
+      const int il = i - d.a_lo;
+      int n[EPL], nmax = 0;
+      double pix[EPL], piy[EPL], rce[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        n[e] = (k >= 1 && k < K) ? d.cnt[((size_t)b * Nown + il) * K + k] : 0;
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        nmax = n[e] > nmax ? n[e] : nmax;
+        pix[e] = piy[e] = 0.0; rce[e] = 1.0;
+        if (n[e] > 0) { pix[e] = Pc[(size_t)(2 * i) * K + k]; piy[e] = Pc[(size_t)(2 * i + 1) * K + k]; rce[e] = rho * d.rc[k - 1]; }
+      }
+      // candidate walk, software pipelined: the slot data of candidate s2+1 is in flight while the partner positions
+      // of candidate s2 (addresses depend on cj) are fetched; loads of the EPL steps are independent, stores come last
+      const int* __restrict__ cjp = d.cj;
+      const double* __restrict__ cexp = d.cex;
+      const double* __restrict__ ceyp = d.cey;
+      const double* __restrict__ cbp = d.cb;
+      const size_t tb = ((size_t)b * Nown + il) * K + k0;
+      int jn[EPL];
+      double exn[EPL], eyn[EPL], cbn[EPL], l0n[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        jn[e] = 0; exn[e] = eyn[e] = cbn[e] = l0n[e] = 0.0;
+        if (0 < n[e]) { const size_t o = tb + e; jn[e] = cjp[o]; exn[e] = cexp[o]; eyn[e] = ceyp[o]; cbn[e] = cbp[o]; l0n[e] = lamc[o]; }
+      }
+      for (int s2 = 0; s2 < nmax; ++s2) {
+        int jc[EPL];
+        double exc[EPL], eyc[EPL], cbc[EPL], l0c[EPL], pjx[EPL], pjy[EPL], l1v[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { jc[e] = jn[e]; exc[e] = exn[e]; eyc[e] = eyn[e]; cbc[e] = cbn[e]; l0c[e] = l0n[e]; }
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          pjx[e] = pjy[e] = 0.0;
+          if (s2 < n[e]) { const int k = k0 + e; pjx[e] = Pc[(size_t)(2 * jc[e]) * K + k]; pjy[e] = Pc[(size_t)(2 * jc[e] + 1) * K + k]; }
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (s2 + 1 < n[e]) { const size_t o = (size_t)(s2 + 1) * T + tb + e; jn[e] = cjp[o]; exn[e] = cexp[o]; eyn[e] = ceyp[o]; cbn[e] = cbp[o]; l0n[e] = lamc[o]; }
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          l1v[e] = 0.0;
+          if (s2 < n[e]) {
+            const double g = exc[e] * (pix[e] - pjx[e]) + eyc[e] * (piy[e] - pjy[e]);
+            const double l1 = fmax(0.0, l0c[e] + 0.5 * rce[e] * (cbc[e] - g));
+            l1v[e] = l1;
+            const double ea = ax ? eyc[e] : exc[e];
+            fz[e] += (2.0 * l1 - l0c[e]) * ea;
+            if (CHK) { fyo[e] += l1 * ea; worst = fmax(worst, fabs(l1 - l0c[e]) / rce[e]); }
+          }
+        }
+        if (ax == 0) {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) if (s2 < n[e]) lamn[(size_t)s2 * T + tb + e] = l1v[e];
+        }
+      }
+    }
+    if (!staged) {
+      if (vec) __pipeline_wait_prior(0);
+      __syncthreads();
+      staged = true;
+    }
+    if (!live) break;
+    // ---- 2. this warp's axis of agent i
+    {
+      const int q = 2 * i + ax;
+      const size_t row = ((size_t)b * d.Qs + q) * K;
+      const size_t q2 = (size_t)b * d.Q + q;
+      const double v0q = d.v0[q2], p0q = d.p0[q2];
+      const double lv = -vl - v0q, uv = vl - v0q;
+      const double plo = d.pb.space[ax], phi = d.pb.space[2 + ax];
+      double xo[EPL], va[EPL], vj[EPL], vv[EPL], vp[EPL], pc1[EPL], off[EPL];
+      load_row<EPL>(d.x + row, k0, K, vec, xo);
+      if (BOX) {
+        if (on & 2) load_row<EPL>(d.va + row, k0, K, vec, va);
+        if (on & 1) load_row<EPL>(d.vj + row, k0, K, vec, vj);
+        if (on & 4) load_row<EPL>(d.vv + row, k0, K, vec, vv);
+        if (on & 8) load_row<EPL>(d.vp + row, k0, K, vec, vp);
+      }
+      // previous position of state k+1 (prox term of the padded copies): pc1[e] = Pc[q][k+1]
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { const int k = k0 + e; pc1[e] = (k < K - 1) ? Pc[(size_t)q * K + k + 1] : 0.0; }
+      double sj[EPL], sa[EPL], sv[EPL], sp[EPL], wj[EPL], wa[EPL], r1v[EPL], r1p[EPL], r2p[EPL];
+      // the force on state k+1 enters row k: shift by one step
+      double fnext = __shfl_down_sync(0xffffffffu, fz[0], 1);
+      if (lane == 31) fnext = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        sj[e] = sa[e] = sv[e] = sp[e] = 0.0; wj[e] = wa[e] = r1v[e] = r1p[e] = 0.0; off[e] = 0.0;
+        if (k < K) {
+          if (BOX && (on & 2)) { const double v = va[e], z = clampd(v, -al, al); sa[e] = v - alpha * z; wa[e] = tra[e] * (2 * z - v); }
+          if (k < K - 1) {
+            if (BOX && (on & 1)) { const double v = vj[e], z = clampd(v, -jl, jl); sj[e] = v - alpha * z; wj[e] = trj[e] * (2 * z - v); }
+            if (BOX && (on & 4)) { const double v = vv[e], z = clampd(v, lv, uv); sv[e] = v - alpha * z; r1v[e] = trv[e] * (2 * z - v); }
+            off[e] = p0q + h * (double)(k + 1) * v0q;
+            double wp = trc[e] * (pc1[e] - off[e]) + ((e + 1 < EPL) ? fz[(e + 1 < EPL) ? e + 1 : e] : fnext);
+            if (BOX && (on & 8)) { const double v = vp[e], z = clampd(v, plo - off[e], phi - off[e]); sp[e] = v - alpha * z; wp += trp[e] * (2 * z - v); }
+            r1p[e] = wp;
+          }
+        }
+      }
+      suffix3<EPL>(r1v, r1p, r2p, lane);
+      double wprev = 0.0;
+      if (BOX) { wprev = __shfl_up_sync(0xffffffffu, wj[EPL - 1], 1); if (lane == 0) wprev = 0.0; }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        const double prev = e == 0 ? wprev : wj[e == 0 ? 0 : e - 1];
+        if (k < K) myrhs[k] = sig * xo[e] + (prev - wj[e]) * ih + wa[e] + h * r1v[e] + h * h * (r2p[e] - 0.5 * r1p[e]);
+      }
+      __syncwarp();
+      // x = Nmat rhs + N0 d : lane owns EPL adjacent columns of the symmetric operator (zeros beyond K)
+      const double d0 = d.vf[q2] - v0q, d1 = d.pf[q2] - (p0q + h * (double)K * v0q);
+      double a0[EPL], a1[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { a0[e] = 0.0; a1[e] = 0.0; }
+      {
+        int j = 0;
+#pragma unroll 2
+        for (; j + 1 < K; j += 2) {
+          const double r0 = myrhs[j], r1 = myrhs[j + 1];
+          double n0[EPL], n1[EPL];
+          load_row<EPL>(Nm + (size_t)j * K, k0, K, vec, n0);
+          load_row<EPL>(Nm + (size_t)(j + 1) * K, k0, K, vec, n1);
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) { a0[e] += n0[e] * r0; a1[e] += n1[e] * r1; }
+        }
+        if (j < K) {
+          const double r0 = myrhs[j];
+          double n0[EPL];
+          load_row<EPL>(Nm + (size_t)j * K, k0, K, vec, n0);
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) a0[e] += n0[e] * r0;
+        }
+      }
+      double xn[EPL], c1[EPL], c2[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        xn[e] = (k < K) ? N0[2 * k] * d0 + N0[2 * k + 1] * d1 + (a0[e] + a1[e]) : 0.0;
+        c1[e] = xn[e];
+      }
+      if (CHK) {
+        double m0 = 0.0, m1 = 0.0;
+        for (int jj = lane; jj < K; jj += 32) { const double r = myrhs[jj]; m0 += Qm[jj] * r; m1 += Qm[K + jj] * r; }
+        m0 = warp_sum(m0); m1 = warp_sum(m1);
+        if (lane == 0) {
+          const double* gg = d.gg + (size_t)b * 4;
+          d.mu[((size_t)b * d.Qs + q) * 2] = m0 - (gg[0] * d0 + gg[1] * d1);
+          d.mu[((size_t)b * d.Qs + q) * 2 + 1] = m1 - (gg[1] * d0 + gg[2] * d1);
+        }
+      }
+      __syncwarp();
+      prefix2<EPL>(c1, c2, lane);
+      double xnext = __shfl_down_sync(0xffffffffu, xn[0], 1);
+      if (lane == 31) xnext = 0.0;
+      double nva[EPL], nvj[EPL], nvv[EPL], nvp[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int k = k0 + e;
+        nva[e] = nvj[e] = nvv[e] = nvp[e] = 0.0;
+        if (k < K) {
+          nva[e] = ((on & 2) ? alpha : 1.0) * xn[e] + sa[e];
+          if (CHK) {
+            const double dv = fabs(xn[e] - clampd(nva[e], -al, al));
+            if (on & 2) pr = fmax(pr, dv); else voa = fmax(voa, dv);
+            nr = fmax(nr, fabs(xn[e]));
+          }
+          if (k < K - 1) {
+            const double rv_ = h * c1[e], rp_ = h * h * (c2[e] - 0.5 * c1[e]);
+            const double aj = (((e + 1 < EPL) ? xn[(e + 1 < EPL) ? e + 1 : e] : xnext) - xn[e]) * ih;
+            nvj[e] = ((on & 1) ? alpha : 1.0) * aj + sj[e];
+            nvv[e] = ((on & 4) ? alpha : 1.0) * rv_ + sv[e];
+            nvp[e] = ((on & 8) ? alpha : 1.0) * rp_ + sp[e];
+            Pn[(size_t)q * K + k + 1] = off[e] + rp_;
+            if (CHK) {
+              const double dj = fabs(aj - clampd(nvj[e], -jl, jl)), dv = fabs(rv_ - clampd(nvv[e], lv, uv));
+              const double dp = fabs(rp_ - clampd(nvp[e], plo - off[e], phi - off[e]));
+              if (on & 1) pr = fmax(pr, dj); else voj = fmax(voj, dj);
+              if (on & 4) pr = fmax(pr, dv); else vov = fmax(vov, dv);
+              if (on & 8) pr = fmax(pr, dp); else vop = fmax(vop, dp);
+              nr = fmax(nr, fmax(fabs(aj), fmax(fabs(rv_), fabs(rp_))));
+            }
+          }
+        }
+      }
+      store_row<EPL>(d.x + row, k0, K, vec, xn);
+      if (BOX) {
+        if (on & 2) store_row<EPL>(d.va + row, k0, K, vec, nva);
+        if (on & 1) store_row<EPL>(d.vj + row, k0, K, vec, nvj);
+        if (on & 4) store_row<EPL>(d.vv + row, k0, K, vec, nvv);
+        if (on & 8) store_row<EPL>(d.vp + row, k0, K, vec, nvp);
+      }
+      if (CHK) store_row<EPL>(d.FY + row, k0, K, vec, fyo);
+      __syncwarp();
+    }
+  }
+  if (CHK) {
+    pr = warp_max_nan(fabs(pr)); nr = warp_max_nan(fabs(nr)); worst = warp_max_nan(fabs(worst));
+    voj = warp_max(voj); voa = warp_max(voa); vov = warp_max(vov); vop = warp_max(vop);
+    if (lane == 0) {
+      double* sl = d.slab + (size_t)b * NRED;
+      atomic_max_pos(sl + R_PRI, pr); atomic_max_pos(sl + R_NPRI, nr);
+      if (worst > 0.0) atomic_max_pos(sl + R_PRICOL, worst);
+      if (voj > 0.0) atomic_max_pos(sl + R_VIOLJ, voj);
+      if (voa > 0.0) atomic_max_pos(sl + R_VIOLA, voa);
+      if (vov > 0.0) atomic_max_pos(sl + R_VIOLV, vov);
+      if (vop > 0.0) atomic_max_pos(sl + R_VIOLP, vop);
+    }
+  }
+}
+
+template <int EPL, int CHK>
+__global__ void __launch_bounds__(IT_THREADS, 2) k_iter(const __grid_constant__ Dev d, int apc, int cur) {
+  extern __shared__ double sm[];
+  const State& S = d.st[blockIdx.y];
+  if (S.phase >= 2) return;
+  if (d.a_lo + (int)blockIdx.x * apc >= d.a_hi) return;
+  if (S.on_mask == 0) iter_body<EPL, CHK, 0>(d, S, apc, cur, sm);
+  else iter_body<EPL, CHK, 1>(d, S, apc, cur, sm);
 }
 
 // ---------------------------------------------------------------------------------- dual residual
@@ -781,7 +1139,7 @@ __global__ void k_control1(const __grid_constant__ Dev d) {
     int add = 0;
     for (int c = 0; c < 4; ++c) if (!(S.on_mask & (1 << c)) && viol[c] > ea + er * npri) add |= 1 << c;
     if (add) {
-      S.on_mask |= add; S.flags |= FL_FACTOR; solved = 0;
+      S.on_mask |= add; S.flags |= FL_FACTOR | FL_RESET; S.reset_mask = add; solved = 0;
       S.it_mark = S.qp_it; S.pri_mark = INFINITY;
       r.rebuilds++;
     }
@@ -867,7 +1225,7 @@ __global__ void k_control2(const __grid_constant__ Dev d) {
     S.flags |= FL_FINISH;
   } else if (next_iter) {
     S.phase = 1; S.rho = d.pb.rho0; S.margin = d.pb.cand_margin; S.attempt = 0; S.have_state = 0;
-    S.flags |= FL_SNAPSHOT | FL_BUILD | FL_RESET;
+    S.flags |= FL_SNAPSHOT | FL_BUILD | FL_RESET; S.reset_mask = 15;
     start_qp(S, d);
   }
 }
@@ -944,7 +1302,8 @@ struct scp_b200_stream {
   scp_b200_record* rec_own = nullptr;
   void* io = nullptr;             // device staging of the host-buffer entry point
   size_t io_bytes = 0;
-  int qpc = 8, nblk_q = 1, epl = 1;
+  int qpc = 8, nblk_q = 1, epl = 1, apc = 4, nblk_a = 1;
+  size_t smem_iter = 0;
   size_t smem_axis = 0, smem_factor = 0;
   long long macro_steps = 0;
 };
@@ -981,6 +1340,18 @@ void launch_axis(scp_b200_stream* s, cudaStream_t st) {
     case 2: ss::k_axis<2, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
     case 3: ss::k_axis<3, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
     default: ss::k_axis<4, MODE><<<grid, ss::AX_THREADS, smem, st>>>(d, s->qpc); break;
+  }
+}
+
+template <int CHK>
+void launch_iter(scp_b200_stream* s, cudaStream_t st, int cur) {
+  const ss::Dev& d = s->d;
+  dim3 grid(s->nblk_a, d.B);
+  switch (s->epl) {
+    case 1: ss::k_iter<1, CHK><<<grid, ss::IT_THREADS, s->smem_iter, st>>>(d, s->apc, cur); break;
+    case 2: ss::k_iter<2, CHK><<<grid, ss::IT_THREADS, s->smem_iter, st>>>(d, s->apc, cur); break;
+    case 3: ss::k_iter<3, CHK><<<grid, ss::IT_THREADS, s->smem_iter, st>>>(d, s->apc, cur); break;
+    default: ss::k_iter<4, CHK><<<grid, ss::IT_THREADS, s->smem_iter, st>>>(d, s->apc, cur); break;
   }
 }
 
@@ -1056,7 +1427,8 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   ss::Dev& d = s->d;
   memset(&d, 0, sizeof(d));
   d.pb = *prob;
-  d.pb.max_admm_iter = ((prob->max_admm_iter + prob->check_every - 1) / prob->check_every) * prob->check_every;
+  d.pb.check_every = prob->check_every + (prob->check_every & 1);      // even: the position ping-pong ends each check period in buffer 0
+  d.pb.max_admm_iter = ((prob->max_admm_iter + d.pb.check_every - 1) / d.pb.check_every) * d.pb.check_every;
   d.B = B; d.N = N; d.K = K; d.Q = 2 * N; d.G = world; d.rank = rank; d.maxc = max_candidates;
   const int nper = (N + world - 1) / world;
   d.Npad = nper * world; d.Qs = 2 * d.Npad;
@@ -1086,7 +1458,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
     for (int c = 0; c < 4; ++c) d.Bc[c] = d.rc + K + (size_t)c * K * K;
   }
   const size_t QK = (size_t)B * d.Qs * K;
-  double** arrs[] = {&d.x, &d.xprev, &d.va, &d.vj, &d.vv, &d.vp, &d.P, &d.Pbar, &d.F, &d.FY};
+  double** arrs[] = {&d.x, &d.xprev, &d.va, &d.vj, &d.vv, &d.vp, &d.P, &d.P1, &d.Pbar, &d.F, &d.FY};
   for (double** a : arrs) if ((rc = dev_alloc(s, a, QK))) return fail(rc);
   if ((rc = dev_alloc(s, &d.mu, (size_t)B * d.Qs * 2))) return fail(rc);
   if ((rc = dev_alloc(s, &d.qsum, (size_t)B * d.Qs * 3))) return fail(rc);
@@ -1097,7 +1469,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   const size_t T = (size_t)B * (Nown > 0 ? Nown : 1) * K;
   if ((rc = dev_alloc(s, &d.cnt, T))) return fail(rc);
   if ((rc = dev_alloc(s, &d.cj, T * d.maxc))) return fail(rc);
-  double** carr[] = {&d.cex, &d.cey, &d.cb, &d.lam};
+  double** carr[] = {&d.cex, &d.cey, &d.cb, &d.lam, &d.lam1};
   for (double** a : carr) if ((rc = dev_alloc(s, a, T * d.maxc))) return fail(rc);
   if ((rc = dev_alloc(s, &d.slab, (size_t)B * ss::NRED))) return fail(rc);
   if (world > 1) { if ((rc = dev_alloc(s, &d.gath, (size_t)world * B * ss::NRED))) return fail(rc); }
@@ -1138,6 +1510,21 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   set_axis_smem(ss::k_axis<3, 0>, s->smem_axis); set_axis_smem(ss::k_axis<3, 1>, s->smem_axis);
   set_axis_smem(ss::k_axis<4, 0>, s->smem_axis); set_axis_smem(ss::k_axis<4, 1>, s->smem_axis);
   set_axis_smem(ss::k_factor, s->smem_factor);
+  {  // fused iteration kernel: one warp per agent, 4 warps per CTA, about two CTAs per SM over the whole batch
+    const int nwarp = ss::IT_THREADS / 64;   // agents in flight per CTA (two warps each)
+    int nba = (2 * sms + B - 1) / B;
+    const int nbamax = (Nown + nwarp - 1) / nwarp;
+    if (nba > nbamax) nba = nbamax;
+    if (nba < 1) nba = 1;
+    int apc = Nown > 0 ? (Nown + nba - 1) / nba : nwarp;
+    apc = ((apc + nwarp - 1) / nwarp) * nwarp;
+    s->apc = apc; s->nblk_a = Nown > 0 ? (Nown + apc - 1) / apc : 1;
+    s->smem_iter = ((size_t)K * K + (size_t)(ss::IT_THREADS / 32) * (K + (K & 1))) * sizeof(double);
+    set_axis_smem(ss::k_iter<1, 0>, s->smem_iter); set_axis_smem(ss::k_iter<1, 1>, s->smem_iter);
+    set_axis_smem(ss::k_iter<2, 0>, s->smem_iter); set_axis_smem(ss::k_iter<2, 1>, s->smem_iter);
+    set_axis_smem(ss::k_iter<3, 0>, s->smem_iter); set_axis_smem(ss::k_iter<3, 1>, s->smem_iter);
+    set_axis_smem(ss::k_iter<4, 0>, s->smem_iter); set_axis_smem(ss::k_iter<4, 1>, s->smem_iter);
+  }
   if (world > 1) {
     ss::NcclApi* api = ss::nccl_api();
     if (!api) return fail(scp_b200_set_error(3, "libnccl.so.2 not found (set SCP_B200_NCCL_LIB)"));
@@ -1174,8 +1561,9 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   const dim3 g_ik((Nown * K + 255) / 256 > 0 ? (Nown * K + 255) / 256 : 1, B);
   const dim3 g_b((B + 127) / 128);
   const size_t pslice = (size_t)(d.Qs / G) * K;            // doubles per rank in the position all-gather (B == 1 when G > 1)
-  auto gather_positions = [&]() -> int {
-    if (G > 1) SS_NCCL(api->AllGather(d.P + (size_t)d.rank * pslice, d.P, pslice, ncclFloat64, s->comm, st));
+  auto gather_positions = [&](int buf) -> int {
+    double* P = buf ? d.P1 : d.P;
+    if (G > 1) SS_NCCL(api->AllGather(P + (size_t)d.rank * pslice, P, pslice, ncclFloat64, s->comm, st));
     return 0;
   };
   auto exchange = [&]() -> int {
@@ -1192,14 +1580,14 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   s->h_done[0] = s->h_done[1] = 0;
   int rc = 0;
   auto body = [&]() -> int {
+    // iteration it reads positions from buffer (it-1)&1 and writes buffer it&1; check is even, so the check
+    // iteration leaves the current positions in buffer 0 (d.P), where every other kernel reads them
     for (int it = 1; it < check; ++it) {
-      launch_axis<0>(s, st);
-      if ((rc = gather_positions())) return rc;
-      ss::k_collide<0><<<g_ik, 256, 0, st>>>(d);
+      launch_iter<0>(s, st, (it - 1) & 1);
+      if ((rc = gather_positions(it & 1))) return rc;
     }
-    launch_axis<1>(s, st);
-    if ((rc = gather_positions())) return rc;
-    ss::k_collide<1><<<g_ik, 256, 0, st>>>(d);
+    launch_iter<1>(s, st, (check - 1) & 1);
+    if ((rc = gather_positions(check & 1))) return rc;
     launch_dual(s, st);
     ss::k_local_sums<<<(B * 32 + 127) / 128, 128, 0, st>>>(d);
     if ((rc = exchange())) return rc;
@@ -1225,7 +1613,7 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
     s->graph_state = -1;
     if (!(env && env[0] == '0')) {
       if (G > 1) {   // NCCL sets up its connections on the first collective: keep that out of the capture
-        if ((rc = gather_positions())) return rc;
+        if ((rc = gather_positions(0))) return rc;
         if ((rc = exchange())) return rc;
       }
       SS_CUDA(cudaStreamSynchronize(st));
