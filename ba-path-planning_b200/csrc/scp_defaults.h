@@ -31,6 +31,6 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->polish_rounds = 40;
   p->team_mode = 0;
   p->lazy_rows = 1;
-  p->reserved5 = 0;
+  p->momentum_pct = 0;
 }
 #endif

@@ -66,7 +66,7 @@ struct Dev {
   double *Nmat, *N0, *Qm, *gg;
   const double *p0, *v0, *pf, *vf;
   int *cnt, *cj;
-  double *cex, *cey, *cb, *lam, *lam1;   // lam / lam1: multiplier ping-pong (lam is current between check periods)
+  double *cex, *cey, *cb, *lam, *lam1, *lamt;   // lam / lam1: multiplier ping-pong (lam is current between check periods)
   double *slab, *gath;
   State* st;
   scp_b200_record* rec;
@@ -527,6 +527,8 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   const double cpr = (double)S.copies * rho;
   const double alpha = d.pb.relax_pct > 0 ? 0.01 * (double)d.pb.relax_pct : 1.0;
   const int on = BOX ? S.on_mask : 0;
+  // heavy-ball extrapolation of the collision state (positions in the prox term, forces, multipliers); only without box rows
+  const double beta = (!BOX && S.phase == 1 && d.pb.momentum_pct > 0) ? 0.01 * (double)d.pb.momentum_pct : 0.0;
   const double* N0 = d.N0 + (size_t)b * 2 * K;
   const double* Qm = d.Qm + (size_t)b * 2 * K;
   const double* Pc = (cur ? d.P1 : d.P) + (size_t)b * d.Qs * K;
@@ -612,7 +614,13 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
         }
         if (ax == 0) {
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) if (s2 < n[e]) lamn[(size_t)s2 * T + tb + e] = l1v[e];
+          for (int e = 0; e < EPL; ++e)
+            if (s2 < n[e]) {
+              const size_t o = (size_t)s2 * T + tb + e;
+              double lh = l1v[e];
+              if (beta > 0.0) { lh = fmax(0.0, l1v[e] + beta * (l1v[e] - d.lamt[o])); d.lamt[o] = l1v[e]; }
+              lamn[o] = lh;
+            }
         }
       }
     }
@@ -641,6 +649,18 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
       // previous position of state k+1 (prox term of the padded copies): pc1[e] = Pc[q][k+1]
 #pragma unroll
       for (int e = 0; e < EPL; ++e) { const int k = k0 + e; pc1[e] = (k < K - 1) ? Pc[(size_t)q * K + k + 1] : 0.0; }
+      if (beta > 0.0) {
+        // own row of the other buffer still holds the positions of two iterations ago; forces of the last one are in F
+        double fold[EPL];
+        load_row<EPL>(d.F + row, k0, K, vec, fold);
+        store_row<EPL>(d.F + row, k0, K, vec, fz);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int k = k0 + e;
+          if (k < K - 1) pc1[e] += beta * (pc1[e] - Pn[(size_t)q * K + k + 1]);
+          fz[e] += beta * (fz[e] - fold[e]);
+        }
+      }
       double sj[EPL], sa[EPL], sv[EPL], sp[EPL], wj[EPL], wa[EPL], r1v[EPL], r1p[EPL], r2p[EPL];
       // the force on state k+1 enters row k: shift by one step
       double fnext = __shfl_down_sync(0xffffffffu, fz[0], 1);
@@ -952,7 +972,7 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
             double ex, ey, bound;
             linearise_pair(dx, dy, i, j, R, ex, ey, bound);
             const size_t o = (size_t)n * T + t;
-            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0;
+            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0; d.lamt[o] = 0.0;
             ++n;
           } else over = 1;
         }
@@ -1017,7 +1037,7 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Dev d) {
             if (!carried) {
               if (n < d.maxc) {
                 const size_t o = (size_t)n * T + t;
-                d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0;
+                d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0; d.lamt[o] = 0.0;
                 ++n; bad += 1.0;
               } else over = 1.0;
             }
@@ -1469,7 +1489,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   const size_t T = (size_t)B * (Nown > 0 ? Nown : 1) * K;
   if ((rc = dev_alloc(s, &d.cnt, T))) return fail(rc);
   if ((rc = dev_alloc(s, &d.cj, T * d.maxc))) return fail(rc);
-  double** carr[] = {&d.cex, &d.cey, &d.cb, &d.lam, &d.lam1};
+  double** carr[] = {&d.cex, &d.cey, &d.cb, &d.lam, &d.lam1, &d.lamt};
   for (double** a : carr) if ((rc = dev_alloc(s, a, T * d.maxc))) return fail(rc);
   if ((rc = dev_alloc(s, &d.slab, (size_t)B * ss::NRED))) return fail(rc);
   if (world > 1) { if ((rc = dev_alloc(s, &d.gath, (size_t)world * B * ss::NRED))) return fail(rc); }

@@ -53,7 +53,7 @@ class Problem(C.Structure):
         ("polish_rounds", C.c_int32),
         ("team_mode", C.c_int32),
         ("lazy_rows", C.c_int32),
-        ("reserved5", C.c_int32),
+        ("momentum_pct", C.c_int32),
     ]
 
 

@@ -73,8 +73,17 @@ def run_batch(N, cfg, n_trials, seeds=None):
         starts.append(p0)
         goals.append(pf)
         used.append(None if seeds is None else seeds[t])
-    solver = BatchSolver(N, cfg["time_horizon"], cfg["time_step"], cfg["min_distance"], cfg["space_dims"],
-                         max_scp_iter=cfg["max_iterations"])
+    from ..solvers.scp import use_stream_engine
+
+    K = int(cfg["time_horizon"] / cfg["time_step"])
+    if use_stream_engine(cfg.get("engine", "auto"), N, K):
+        from ..solvers.stream import StreamSolver
+
+        solver = StreamSolver(N, cfg["time_horizon"], cfg["time_step"], cfg["min_distance"], cfg["space_dims"],
+                              n_scenarios=n_trials, max_scp_iter=cfg["max_iterations"])
+    else:
+        solver = BatchSolver(N, cfg["time_horizon"], cfg["time_step"], cfg["min_distance"], cfg["space_dims"],
+                             max_scp_iter=cfg["max_iterations"])
     t0 = time.perf_counter()
     _, recs = solver.solve(np.stack(starts), np.stack(goals))
     dt = time.perf_counter() - t0

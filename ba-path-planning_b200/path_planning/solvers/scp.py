@@ -18,6 +18,17 @@ import numpy as np
 from .. import _capi
 
 
+def use_stream_engine(engine, n_agents, n_steps):
+    """"auto": scenarios whose state cannot live in one CTA's shared memory (2NK doubles per array; the one-CTA
+    solver then works out of L2 and the whole-grid kernel pays grid barriers) go to the streaming solver, which
+    needs K <= 128; config 1 (K=500) and small scenarios stay on the one-CTA / whole-grid solver."""
+    if engine == "stream":
+        return True
+    if engine == "cta":
+        return False
+    return n_steps <= 128 and 2 * n_agents * n_steps >= 8192
+
+
 class SCP:
     def __init__(self, n_vehicles=5, time_horizon=3.0, time_step=0.1, min_distance=0.1, space_dims=None):
         self.N = n_vehicles
@@ -41,6 +52,7 @@ class SCP:
         self.jerk_min, self.jerk_max = -20, 20
         # new, additive: solver settings (fields of scp_b200_problem), device index, last record
         self.solver_settings = {}
+        self.engine = "auto"   # "cta": one CTA / whole grid per scenario; "stream": streaming multi-kernel solver; "auto"
         self.device = 0
         self.verbose = True
         self.last_record = None
@@ -102,10 +114,13 @@ class SCP:
         vel = np.empty((N, K, 2))
         rec = _capi.Record()
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _capi.check(lib.scp_b200_solve_batch_host(C.byref(p), 1, ptr(p0), ptr(v0), ptr(pf), ptr(vf), ptr(acc),
-                                                  ptr(pos), ptr(vel), C.cast(C.byref(rec), C.c_void_p),
-                                                  int(self.device)))
-        r = _capi.record_to_dict(rec)
+        if use_stream_engine(self.engine, N, K):
+            r = self._solve_streaming(max_iterations, p0, v0, pf, vf, acc, pos, vel)
+        else:
+            _capi.check(lib.scp_b200_solve_batch_host(C.byref(p), 1, ptr(p0), ptr(v0), ptr(pf), ptr(vf), ptr(acc),
+                                                      ptr(pos), ptr(vel), C.cast(C.byref(rec), C.c_void_p),
+                                                      int(self.device)))
+            r = _capi.record_to_dict(rec)
         self.last_record = r
         if r["status"] == _capi.STATUS_INITIAL_QP_FAILED:
             print("not feasible")
@@ -124,6 +139,27 @@ class SCP:
         self.trajectories = {"positions": pos, "velocities": vel, "accelerations": acc}
         self._say(f"Trajectory generation completed in {time.time() - start:.3f} seconds")
         return self.trajectories
+
+    def _solve_streaming(self, max_iterations, p0, v0, pf, vf, acc, pos, vel):
+        """Large scenarios: the streaming solver (include/scp_b200.h, scp_b200_stream_*), host buffers in and out."""
+        import torch
+
+        from .stream import StreamSolver
+
+        with torch.cuda.device(int(self.device)):
+            settings = dict(self.solver_settings, max_scp_iter=int(max_iterations), vel_limit=float(self.vel_max),
+                            acc_limit=float(self.acc_max), jerk_limit=float(self.jerk_max),
+                            scp_tolerance=float(self.convergence_tolerance))
+            s = StreamSolver(self.N, self.T, self.h, self.R, self.space_dims, n_scenarios=1, **settings)
+            traj, recs = s.solve(p0.reshape(1, self.N, 2), pf.reshape(1, self.N, 2), v0.reshape(1, self.N, 2),
+                                 vf.reshape(1, self.N, 2))
+            s.close()
+        acc[...] = traj["accelerations"][0]
+        pos[...] = traj["positions"][0]
+        vel[...] = traj["velocities"][0]
+        r = recs[0]
+        r["device_ms"] = s.last_device_ms
+        return r
 
     # Plotting is out of scope for acceleration; thin pass-throughs keep the entry points alive.
     def visualize_trajectories(self, show_animation=False, save_path="trajectories.pdf"):

@@ -67,7 +67,7 @@ typedef struct scp_b200_problem {
   int32_t lazy_rows;       /* streaming solver: 1 = the box-row classes (jerk, acc, vel, pos) start outside the ADMM and a
                               class joins, per scenario, when a converged iterate violates it (verify-and-enlarge, as
                               for the collision rows); 0 = all box rows carried from the start */
-  int32_t reserved5;
+  int32_t momentum_pct;    /* streaming solver: heavy-ball extrapolation of the collision state in percent (0: off) */
 } scp_b200_problem;
 
 /* Per-scenario result record (device or host array of B records). */

@@ -69,6 +69,26 @@ def test_stream_matches_golden(torch_cuda, path):
           f"ADMM iterations {r['admm_iterations']}, device {ms:.1f} ms")
 
 
+def test_public_class_streaming_engine(torch_cuda):
+    """`SCP(...).generate_trajectories()` with engine="stream": same contract (result dict, record, prints) as the
+    default engine, trajectories within tolerance of the certified golden; "auto" picks it for large scenarios."""
+    from path_planning import SCP
+    from path_planning.solvers.scp import use_stream_engine
+
+    g = np.load([p for p in golden_cases() if p.endswith("n8_s1.npz")][0])
+    s = SCP(n_vehicles=int(g["N"]), time_horizon=float(g["T"]), time_step=float(g["h"]), min_distance=float(g["R"]),
+            space_dims=list(g["space"]))
+    s.verbose = False
+    s.engine = "stream"
+    s.set_initial_states(g["p0"])
+    s.set_final_states(g["pf"])
+    tr = s.generate_trajectories(max_iterations=15)
+    assert set(tr) == {"positions", "velocities", "accelerations"} and tr["positions"].shape == (int(g["N"]), 50, 2)
+    perr = np.linalg.norm(tr["positions"] - g["positions"]) / np.linalg.norm(g["positions"])
+    assert perr <= POS_TOL and s.last_record["scp_iterations"] == int(g["iterations"])
+    assert use_stream_engine("auto", 200, 100) and not use_stream_engine("auto", 10, 500) and not use_stream_engine("auto", 25, 50)
+
+
 def test_stream_batch_equals_single(torch_cuda):
     """Scenarios of a batch do not influence each other: batch results == one-by-one results, bit for bit."""
     from path_planning.scenarios.position_generator import generate_positions
