@@ -455,6 +455,17 @@ __device__ __forceinline__ void load_row(const double* __restrict__ p, int k0, i
     for (int e = 0; e < EPL; ++e) v[e] = (k0 + e < K) ? p[k0 + e] : 0.0;
   }
 }
+// no bounds check: the caller guarantees k0 .. k0+EPL-1 are readable (the staged operator is padded by EPL doubles)
+template <int EPL>
+__device__ __forceinline__ void load_row_nc(const double* __restrict__ p, int k0, bool vec, double (&v)[EPL]) {
+  if ((EPL & 1) == 0 && vec) {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) { const double2 t = *reinterpret_cast<const double2*>(p + k0 + e); v[e] = t.x; v[e + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) v[e] = p[k0 + e];
+  }
+}
 template <int EPL>
 __device__ __forceinline__ void store_row(double* __restrict__ p, int k0, int K, bool vec, const double (&v)[EPL]) {
   if ((EPL & 1) == 0 && vec) {
@@ -511,8 +522,9 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   const int ia = d.a_lo + blockIdx.x * apc, ib = min(ia + apc, d.a_hi);
   const int ax = warp & 1;                                    // two warps per agent: one per axis
   double* Nm = sm;
-  double* myrhs = sm + (size_t)K * K + (size_t)warp * (K + (K & 1));
+  double* myrhs = sm + (size_t)K * K + 4 + (size_t)warp * (K + (K & 1));   // 4 doubles of padding behind the operator
   const bool vec = (K & 1) == 0;
+  if (threadIdx.x < 4) sm[(size_t)K * K + threadIdx.x] = 0.0;
   {  // operator -> shared memory, asynchronously (cp.async 16 B) when rows are 16-byte aligned
     const double* src = d.Nmat + (size_t)b * K * K;
     if (vec) {
@@ -697,20 +709,24 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
 #pragma unroll
       for (int e = 0; e < EPL; ++e) { a0[e] = 0.0; a1[e] = 0.0; }
       {
+        // lanes beyond K read column 0 (discarded below); a lane straddling K reads into the next row / the padding
+        const int kc = (k0 < K) ? k0 : 0;
+        const double* np = Nm + kc;
         int j = 0;
 #pragma unroll 2
         for (; j + 1 < K; j += 2) {
           const double r0 = myrhs[j], r1 = myrhs[j + 1];
           double n0[EPL], n1[EPL];
-          load_row<EPL>(Nm + (size_t)j * K, k0, K, vec, n0);
-          load_row<EPL>(Nm + (size_t)(j + 1) * K, k0, K, vec, n1);
+          load_row_nc<EPL>(np, 0, vec, n0);
+          load_row_nc<EPL>(np + K, 0, vec, n1);
 #pragma unroll
           for (int e = 0; e < EPL; ++e) { a0[e] += n0[e] * r0; a1[e] += n1[e] * r1; }
+          np += 2 * K;
         }
         if (j < K) {
           const double r0 = myrhs[j];
           double n0[EPL];
-          load_row<EPL>(Nm + (size_t)j * K, k0, K, vec, n0);
+          load_row_nc<EPL>(np, 0, vec, n0);
 #pragma unroll
           for (int e = 0; e < EPL; ++e) a0[e] += n0[e] * r0;
         }
@@ -1539,7 +1555,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
     int apc = Nown > 0 ? (Nown + nba - 1) / nba : nwarp;
     apc = ((apc + nwarp - 1) / nwarp) * nwarp;
     s->apc = apc; s->nblk_a = Nown > 0 ? (Nown + apc - 1) / apc : 1;
-    s->smem_iter = ((size_t)K * K + (size_t)(ss::IT_THREADS / 32) * (K + (K & 1))) * sizeof(double);
+    s->smem_iter = ((size_t)K * K + 4 + (size_t)(ss::IT_THREADS / 32) * (K + (K & 1))) * sizeof(double);
     set_axis_smem(ss::k_iter<1, 0>, s->smem_iter); set_axis_smem(ss::k_iter<1, 1>, s->smem_iter);
     set_axis_smem(ss::k_iter<2, 0>, s->smem_iter); set_axis_smem(ss::k_iter<2, 1>, s->smem_iter);
     set_axis_smem(ss::k_iter<3, 0>, s->smem_iter); set_axis_smem(ss::k_iter<3, 1>, s->smem_iter);

@@ -76,7 +76,7 @@ def run_batch(N, cfg, n_trials, seeds=None):
     from ..solvers.scp import use_stream_engine
 
     K = int(cfg["time_horizon"] / cfg["time_step"])
-    if use_stream_engine(cfg.get("engine", "auto"), N, K):
+    if use_stream_engine(cfg.get("engine", "auto"), N, K, n_trials):
         from ..solvers.stream import StreamSolver
 
         solver = StreamSolver(N, cfg["time_horizon"], cfg["time_step"], cfg["min_distance"], cfg["space_dims"],
