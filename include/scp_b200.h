@@ -183,7 +183,7 @@ int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents,
 typedef struct scp_b200_stream scp_b200_stream;
 
 /* scp_b200_default_problem with the ADMM settings that suit the streaming solver (fixed rho, over-relaxation 1.6,
- * eps 1e-4, iteration cap 20000, lazy box rows). */
+ * eps 1e-4, iteration cap 20000, lazy box rows, rho0 = clamp((50/K)^2, 0.1, 1), stall window 1000). */
 void scp_b200_stream_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon,
                                      double time_step, double min_distance);
 
