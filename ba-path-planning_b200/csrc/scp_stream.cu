@@ -73,6 +73,12 @@ struct Dev {
   double *acc, *pos, *vel;     // (B, Npad, K, 2)
   int Npad;
   int* done;
+  // peer-memory exchange of the position slices (agent sharding without a per-iteration NCCL call)
+  int p2p;
+  double* peerP[8];            // P of every rank (own entry = local pointer)
+  double* peerP1[8];
+  unsigned* peerFlag[8];       // flag arrays of every rank: flag[g] = k_iter launches rank g has completed and published
+  unsigned *flag, *iter_no, *cta_done, *err;
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -513,6 +519,23 @@ __device__ __forceinline__ void prefix2(double (&b)[EPL], double (&c)[EPL], int 
   for (int e = 0; e < EPL; ++e) { c[e] += c2 + (double)(e + 1) * c1; b[e] += c1; }
 }
 
+constexpr long long P2P_SPIN_LIMIT = 6000000000LL;   // ~3 s: a lost peer must not hang the box
+
+// positions of launch n (buffer `cur`) are complete, and every peer has finished reading the buffer this launch
+// overwrites, once every peer has published launch n
+__device__ __forceinline__ void p2p_wait(const Dev& d) {
+  const unsigned n = *(volatile unsigned*)d.iter_no;
+  const long long t0 = clock64();
+  for (int g = 0; g < d.G; ++g) {
+    if (g == d.rank) continue;
+    while (*(volatile unsigned*)(d.flag + g) < n) {
+      if (clock64() - t0 > P2P_SPIN_LIMIT) { *d.err = 1u; break; }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+}
+
 // BOX = 0: no box-row class is carried by this scenario's ADMM (the usual state with lazy rows) -- all box code
 // compiles away and only x and the positions move through memory.
 template <int EPL, int CHK, int BOX>
@@ -533,6 +556,10 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
     } else {
       for (int e = threadIdx.x; e < K * K; e += blockDim.x) Nm[e] = src[e];
     }
+  }
+  if (d.p2p) {
+    if (threadIdx.x == 0) p2p_wait(d);
+    __syncthreads();
   }
   const double h = d.pb.time_step, ih = 1.0 / h, rho = S.rho, sig = d.pb.sigma;
   const double vl = d.pb.vel_limit, al = d.pb.acc_limit, jl = d.pb.jerk_limit;
@@ -771,6 +798,10 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
             nvv[e] = ((on & 4) ? alpha : 1.0) * rv_ + sv[e];
             nvp[e] = ((on & 8) ? alpha : 1.0) * rp_ + sp[e];
             Pn[(size_t)q * K + k + 1] = off[e] + rp_;
+            if (d.p2p) {   // the own slice goes straight into every peer's buffer over NVLink (B = 1 when sharded)
+              for (int g = 0; g < d.G; ++g)
+                if (g != d.rank) (cur ? d.peerP[g] : d.peerP1[g])[(size_t)q * K + k + 1] = off[e] + rp_;
+            }
             if (CHK) {
               const double dj = fabs(aj - clampd(nvj[e], -jl, jl)), dv = fabs(rv_ - clampd(nvv[e], lv, uv));
               const double dp = fabs(rp_ - clampd(nvp[e], plo - off[e], phi - off[e]));
@@ -806,6 +837,23 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
       if (vop > 0.0) atomic_max_pos(sl + R_VIOLP, vop);
     }
   }
+  if (d.p2p) {
+    // publish: all stores of this CTA (local and remote) are ordered before the flag; the last CTA of the launch
+    // bumps the launch counter and writes it into every peer's flag array
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned fin = atomicAdd(d.cta_done, 1u);
+      if (fin == gridDim.x - 1) {
+        *(volatile unsigned*)d.cta_done = 0u;
+        const unsigned n = *(volatile unsigned*)d.iter_no + 1u;
+        *(volatile unsigned*)d.iter_no = n;
+        __threadfence_system();
+        for (int g = 0; g < d.G; ++g)
+          if (g != d.rank) *(volatile unsigned*)(d.peerFlag[g] + d.rank) = n;
+      }
+    }
+  }
 }
 
 template <int EPL, int CHK>
@@ -816,6 +864,11 @@ __global__ void __launch_bounds__(IT_THREADS, 2) k_iter(const __grid_constant__ 
   if (d.a_lo + (int)blockIdx.x * apc >= d.a_hi) return;
   if (S.on_mask == 0) iter_body<EPL, CHK, 0>(d, S, apc, cur, sm);
   else iter_body<EPL, CHK, 1>(d, S, apc, cur, sm);
+}
+
+// the kernels after a check iteration read every agent's positions: wait until all peers have published it
+__global__ void k_wait(const __grid_constant__ Dev d) {
+  if (d.p2p && threadIdx.x == 0 && blockIdx.x == 0 && d.st[0].phase < 2) p2p_wait(d);
 }
 
 // ---------------------------------------------------------------------------------- dual residual
@@ -976,6 +1029,15 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
     const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
     if (k >= 1) {
       const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
+      // warm duals: a row carried by the previous subproblem keeps its multiplier (same minimiser, fewer iterations;
+      // the reference restarts OSQP from y = 0 every SCP iteration, scp.py:441-443)
+      int oj[MAXC_MAX];
+      double ol[MAXC_MAX];
+      int on = 0;
+      if (d.pb.warm_duals && S.scp_it > 0) {
+        on = d.cnt[t];
+        for (int s = 0; s < on; ++s) { oj[s] = d.cj[(size_t)s * T + t]; ol[s] = d.lam[(size_t)s * T + t]; }
+      }
       const double* Pb = d.Pbar + (size_t)b * d.Qs * K;
       const double pix = Pb[(size_t)(2 * i) * K + k], piy = Pb[(size_t)(2 * i + 1) * K + k];
       const double R = d.pb.min_distance, r2 = (R + S.margin) * (R + S.margin);
@@ -985,10 +1047,11 @@ __global__ void __launch_bounds__(256) k_build(const __grid_constant__ Dev d) {
         const double dx = pix - Pb[(size_t)(2 * j) * K + k], dy = piy - Pb[(size_t)(2 * j + 1) * K + k];
         if (dx * dx + dy * dy < r2) {
           if (n < d.maxc) {
-            double ex, ey, bound;
+            double ex, ey, bound, l = 0.0;
             linearise_pair(dx, dy, i, j, R, ex, ey, bound);
+            for (int s = 0; s < on; ++s) if (oj[s] == j) l = ol[s];
             const size_t o = (size_t)n * T + t;
-            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = 0.0; d.lamt[o] = 0.0;
+            d.cj[o] = j; d.cex[o] = ex; d.cey[o] = ey; d.cb[o] = bound; d.lam[o] = l; d.lamt[o] = l;
             ++n;
           } else over = 1;
         }
@@ -1330,6 +1393,7 @@ struct scp_b200_stream {
   int* h_done = nullptr;          // pinned, 2 entries
   cudaEvent_t ev[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
   void* tables = nullptr;
+  std::vector<void*> ipc_opened;  // peer mappings (cudaIpcOpenMemHandle)
   cudaStream_t own = nullptr;     // the solver's stream (a captured graph cannot live on the legacy default stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -1439,6 +1503,7 @@ int scp_b200_nccl_unique_id(void* id128) {
 
 void scp_b200_stream_destroy(scp_b200_stream* s) {
   if (!s) return;
+  for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : s->allocs) cudaFree(p);
   if (s->h_done) cudaFreeHost(s->h_done);
   if (s->io) cudaFree(s->io);
@@ -1517,6 +1582,10 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   else d.gath = d.slab;
   if ((rc = dev_alloc(s, &d.st, (size_t)B))) return fail(rc);
   if ((rc = dev_alloc(s, &d.done, 1))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.flag, 16))) return fail(rc);
+  if (cudaMemset(d.flag, 0, 16 * sizeof(unsigned)) != cudaSuccess) return fail(scp_b200_set_error(100, "memset"));
+  d.iter_no = d.flag + 8; d.cta_done = d.flag + 9; d.err = d.flag + 10;
+  d.p2p = 0;
   const size_t OUT = (size_t)B * d.Npad * K * 2;
   if ((rc = dev_alloc(s, &d.acc, OUT))) return fail(rc);
   if ((rc = dev_alloc(s, &d.pos, OUT))) return fail(rc);
@@ -1578,6 +1647,43 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   return 0;
 }
 
+// Peer-memory exchange for the agent-sharded solve: every rank exports IPC handles of its two position buffers and
+// its flag array (3 x 64 bytes), the host all-gathers them, every rank maps its peers'.  After a successful connect
+// k_iter stores the own position slice directly into every peer's buffer over NVLink and a flag per rank replaces
+// the per-iteration ncclAllGather; the check-period slab exchange stays on NCCL.
+int scp_b200_stream_ipc_handles(scp_b200_stream* s, void* out192) {
+  if (!s || !out192) return scp_b200_set_error(1, "null argument");
+  cudaIpcMemHandle_t h[3];
+  SS_CUDA(cudaIpcGetMemHandle(&h[0], s->d.P));
+  SS_CUDA(cudaIpcGetMemHandle(&h[1], s->d.P1));
+  SS_CUDA(cudaIpcGetMemHandle(&h[2], s->d.flag));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(out192, h, sizeof(h));
+  return 0;
+}
+
+int scp_b200_stream_ipc_connect(scp_b200_stream* s, const void* all_handles) {
+  if (!s || !all_handles) return scp_b200_set_error(1, "null argument");
+  ss::Dev& d = s->d;
+  if (d.G < 2 || d.G > 8) return scp_b200_set_error(1, "peer exchange needs 2..8 ranks");
+  if ((d.Npad / d.G) * (d.G - 1) >= d.N) return scp_b200_set_error(1, "peer exchange needs agents on every rank");
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+  for (int g = 0; g < d.G; ++g) {
+    if (g == d.rank) { d.peerP[g] = d.P; d.peerP1[g] = d.P1; d.peerFlag[g] = d.flag; continue; }
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; ++k) {
+      cudaError_t e = cudaIpcOpenMemHandle(&p[k], h[3 * g + k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return scp_b200_set_error(100 + (int)e, (std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)).c_str());
+      s->ipc_opened.push_back(p[k]);
+    }
+    d.peerP[g] = (double*)p[0]; d.peerP1[g] = (double*)p[1]; d.peerFlag[g] = (unsigned*)p[2];
+  }
+  d.p2p = 1;
+  if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+  s->graph_state = 0;      // kernel arguments changed: capture again
+  return 0;
+}
+
 // The whole of SCP.generate_trajectories (scp.py:131-180) for the solver's B scenarios (or for ONE scenario whose
 // agents are sharded over `world` ranks: every rank calls this with the same inputs).  Blocks until finished.
 int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* d_v0, const double* d_pf, const double* d_vf,
@@ -1604,18 +1710,21 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   const size_t pslice = (size_t)(d.Qs / G) * K;            // doubles per rank in the position all-gather (B == 1 when G > 1)
   auto gather_positions = [&](int buf) -> int {
     double* P = buf ? d.P1 : d.P;
-    if (G > 1) SS_NCCL(api->AllGather(P + (size_t)d.rank * pslice, P, pslice, ncclFloat64, s->comm, st));
+    if (G > 1 && !d.p2p) SS_NCCL(api->AllGather(P + (size_t)d.rank * pslice, P, pslice, ncclFloat64, s->comm, st));
     return 0;
   };
   auto exchange = [&]() -> int {
     if (G > 1) SS_NCCL(api->AllGather(d.slab, d.gath, (size_t)B * ss::NRED, ncclFloat64, s->comm, st));
     return 0;
   };
+  int rc0 = 0;
   SS_CUDA(cudaEventRecord(s->t0, st));
   ss::k_init<<<g_elem, 256, 0, st>>>(d);
   ss::k_factor<<<B, 512, s->smem_factor, st>>>(d);
   ss::k_finalize<<<g_b, 128, 0, st>>>(d);
   SS_CUDA(cudaGetLastError());
+  // peer exchange: no rank may push positions into a peer's buffers before that peer's k_init has run
+  if (d.p2p && (rc0 = exchange())) return rc0;
   const int check = d.pb.check_every;
   const long long max_macros = (long long)(d.pb.max_scp_iter + 2) * 22 * (d.pb.max_admm_iter / check + 2);
   s->h_done[0] = s->h_done[1] = 0;
@@ -1629,6 +1738,7 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
     }
     launch_iter<1>(s, st, (check - 1) & 1);
     if ((rc = gather_positions(check & 1))) return rc;
+    if (d.p2p) ss::k_wait<<<1, 32, 0, st>>>(d);
     launch_dual(s, st);
     ss::k_local_sums<<<(B * 32 + 127) / 128, 128, 0, st>>>(d);
     if ((rc = exchange())) return rc;
@@ -1707,6 +1817,11 @@ int scp_b200_stream_solve(scp_b200_stream* s, const double* d_p0, const double* 
   SS_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
   SS_CUDA(cudaStreamSynchronize(st));
   SS_CUDA(cudaGetLastError());
+  if (d.p2p) {
+    unsigned e = 0;
+    SS_CUDA(cudaMemcpy(&e, d.err, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) return scp_b200_set_error(5, "peer exchange timed out waiting for a rank");
+  }
   if (device_ms) SS_CUDA(cudaEventElapsedTime(device_ms, s->t0, s->t1));
   if (macro_steps) *macro_steps = s->macro_steps;
   return 0;

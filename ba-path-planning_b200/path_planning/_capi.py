@@ -131,6 +131,8 @@ _SIGNATURES = {
     "scp_b200_stream_create": (
         C.c_int, [_P(Problem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_void_p)]),
     "scp_b200_stream_destroy": (None, [C.c_void_p]),
+    "scp_b200_stream_ipc_handles": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "scp_b200_stream_ipc_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "scp_b200_stream_solve": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -30,7 +30,7 @@ def agent_block(n_agents: int, rank: int, world: int):
 
 class StreamSolver:
     def __init__(self, n_vehicles, time_horizon, time_step, min_distance, space_dims=None, n_scenarios=1,
-                 max_candidates=16, group=None, sharded=False, **settings):
+                 max_candidates=16, group=None, sharded=False, peer_exchange=False, **settings):
         torch = _require_cuda()
         self.torch = torch
         self.lib = _capi.load()
@@ -62,6 +62,27 @@ class StreamSolver:
             C.byref(self.problem), self.B, int(max_candidates), self.rank, self.world,
             C.cast(idbuf, C.c_void_p) if idbuf is not None else None, C.byref(h)))
         self._h = h
+        self.exchange = "none" if self.world == 1 else "nccl"
+        if self.world > 1 and peer_exchange:
+            # peer-memory exchange of the position slices (NVLink stores + flags) instead of an NCCL call per iteration
+            import torch.distributed as dist
+
+            mine = (C.c_char * 192)()
+            ok = self.lib.scp_b200_stream_ipc_handles(self._h, C.cast(mine, C.c_void_p)) == 0
+            box = [None] * self.world
+            dist.all_gather_object(box, bytes(mine.raw) if ok else None, group=group)
+            if all(b is not None for b in box):
+                blob = (C.c_char * (192 * self.world)).from_buffer_copy(b"".join(box))
+                ok = self.lib.scp_b200_stream_ipc_connect(self._h, C.cast(blob, C.c_void_p)) == 0
+            else:
+                ok = False
+            flags = [None] * self.world
+            dist.all_gather_object(flags, bool(ok), group=group)
+            if all(flags):
+                self.exchange = "peer"
+            elif ok:
+                raise _capi.ScpB200Error("peer exchange connected on some ranks only")
+            dist.barrier(group=group)
         self.last_device_ms = None
         self.last_macro_steps = None
 

@@ -196,6 +196,12 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
                            int world, const void* nccl_id128, scp_b200_stream** out);
 void scp_b200_stream_destroy(scp_b200_stream* solver);
 
+/* Optional, world > 1: replace the per-iteration ncclAllGather of the positions by peer-memory stores over NVLink.
+ * Every rank exports 192 bytes (3 CUDA IPC handles), the host all-gathers them into world x 192 bytes and every rank
+ * connects; on failure (no peer access) the solver keeps using NCCL. */
+int scp_b200_stream_ipc_handles(scp_b200_stream* solver, void* out192);
+int scp_b200_stream_ipc_connect(scp_b200_stream* solver, const void* all_handles);
+
 /* Device buffers as in scp_b200_solve_batch; with world > 1 every rank passes the same full-size
  * inputs and receives the full outputs.  Blocks until finished; *device_ms (optional) is the time
  * between the first and the last operation on `stream`, *macro_steps the check periods run. */

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--seed", type=int, default=10_000)
     ap.add_argument("--repeats", type=int, default=2)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--peer", action="store_true", help="peer-memory exchange of the positions instead of NCCL per iteration")
     ap.add_argument("--set", action="append", default=[], help="solver setting name=value")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -46,7 +47,7 @@ def main():
     N, T, h, R = a.agents, a.horizon, 0.2, 0.8
     p0, pf, space = generate_positions_large(N, R, time_horizon=T)
     d0, d1 = torch.from_numpy(p0[None]).cuda(), torch.from_numpy(pf[None]).cuda()
-    s = StreamSolver(N, T, h, R, space, n_scenarios=1, sharded=world > 1, **settings)
+    s = StreamSolver(N, T, h, R, space, n_scenarios=1, sharded=world > 1, peer_exchange=a.peer, **settings)
     best = None
     for _ in range(a.repeats):
         acc, pos, vel, rec = s.solve_device(d0, d1)
@@ -67,7 +68,7 @@ def main():
                   f"admm {r['admm_iterations']}/{r1['admm_iterations']}", flush=True)
     if rank == 0:
         print(json.dumps({
-            "case": "single scenario, streaming solver", "N": N, "K": s.K, "n_gpus": world, "device_ms": best,
+            "case": "single scenario, streaming solver", "N": N, "K": s.K, "n_gpus": world, "exchange": s.exchange, "device_ms": best,
             "scp_iterations": r["scp_iterations"], "converged": r["converged"], "admm_iterations": r["admm_iterations"],
             "macro_steps": s.last_macro_steps, "qp_unsolved": r["qp_unsolved"], "rebuilds": r["rebuilds"],
             "max_copies": r["max_copies"], "min_separation": r["min_separation"], "objective": r["objective"],
