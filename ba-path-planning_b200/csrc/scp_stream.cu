@@ -840,9 +840,9 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   if (d.p2p) {
     // publish: all stores of this CTA (local and remote) are ordered before the flag; the last CTA of the launch
     // bumps the launch counter and writes it into every peer's flag array
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                 // the CTA's stores happen-before thread 0's system fence (cumulativity)
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned fin = atomicAdd(d.cta_done, 1u);
       if (fin == gridDim.x - 1) {
         *(volatile unsigned*)d.cta_done = 0u;

@@ -170,3 +170,15 @@ def test_stream_agent_sharded_matches_single_gpu(torch_cuda):
         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SHARDED_CHECK_OK" in out.stdout
+
+
+def test_stream_agent_sharded_peer_exchange_matches_single_gpu(torch_cuda):
+    """Same as above with the peer-memory exchange (NVLink stores + flags inside k_iter) instead of NCCL per iteration."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29633", os.path.join(ROOT, "tools", "run_sharded_scenario.py"), "--agents", "30", "--check", "--peer"],
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SHARDED_CHECK_OK" in out.stdout and '"exchange": "peer"' in out.stdout
