@@ -12,8 +12,8 @@
 // copies, one K x K operator per scenario.  No polish here: subproblems end on the ADMM residual test.
 //
 // Reference code replaced (src/path_planning/solvers/scp.py):
-//   k_axis<.,0/1>   x-update + rows of A x           OSQP iteration inside problem.solve() :362,:445
-//   k_collide       collision rows                    rows of _add_collision_constraints   :453-557
+//   k_iter          one ADMM iteration, fused:        OSQP iteration inside problem.solve() :362,:445 with the rows of
+//                   collision rows + x-update + A x   _add_collision_constraints :453-557 (matrix free)
 //   k_build         candidate rows + linearisation    _add_collision_constraints           :487-549
 //   k_scan          gate / min separation / verify    _fast_check_avoidance_constraints    :597-615
 //   k_control*      termination + SCP loop            generate_trajectories                :152-166
@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(512) k_factor(const __grid_constant__ Dev d) {
 }
 
 // ---------------------------------------------------------------------------------- agent-axis kernel
+// (MODE 0/1 are the first, two-kernel form of the iteration -- k_axis + k_collide -- kept for reference and for
+// debugging against k_iter; only MODE 2 is launched.)
 // One warp per (scenario, agent-axis): lanes hold the steps k = lane + 32 e.  MODE 0: one ADMM iteration of the
 // box rows and the x-update (scp_device.inl admm_iter_fused, state streamed from HBM/L2 instead of shared memory);
 // MODE 1: the same plus the primal residual terms and the equality multipliers (check iteration);
@@ -1615,10 +1617,6 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   s->epl = (K + 31) / 32;
   s->smem_axis = ((size_t)K * K + (size_t)(ss::AX_THREADS / 32) * K) * sizeof(double);
   s->smem_factor = ((size_t)K * K + 4 * (size_t)K) * sizeof(double);
-  set_axis_smem(ss::k_axis<1, 0>, s->smem_axis); set_axis_smem(ss::k_axis<1, 1>, s->smem_axis);
-  set_axis_smem(ss::k_axis<2, 0>, s->smem_axis); set_axis_smem(ss::k_axis<2, 1>, s->smem_axis);
-  set_axis_smem(ss::k_axis<3, 0>, s->smem_axis); set_axis_smem(ss::k_axis<3, 1>, s->smem_axis);
-  set_axis_smem(ss::k_axis<4, 0>, s->smem_axis); set_axis_smem(ss::k_axis<4, 1>, s->smem_axis);
   set_axis_smem(ss::k_factor, s->smem_factor);
   {  // fused iteration kernel: one warp per agent, 4 warps per CTA, about two CTAs per SM over the whole batch
     const int nwarp = ss::IT_THREADS / 64;   // agents in flight per CTA (two warps each)
