@@ -160,6 +160,59 @@ def test_stream_large_scenario_properties(torch_cuda):
           f"min separation {r['min_separation']:.4f}")
 
 
+@pytest.mark.parametrize("N,K", [(1, 20), (2, 15), (6, 31), (6, 33), (5, 64), (4, 127), (4, 128)])
+def test_stream_step_counts_and_tiny_scenarios(torch_cuda, N, K):
+    """Every lane layout of k_iter (EPL = 1..4, odd K = scalar rows, K = 128 = all lanes full) and the degenerate
+    sizes (one agent: no pair rows at all) against the one-CTA solver, which ends on KKT certificates."""
+    from oracle import scp_oracle
+    from path_planning.solvers.batch import BatchSolver
+
+    rng = np.random.default_rng(100 * N + K)
+    h, space = 0.2, [0, 0, 12, 12]
+    T = K * h + 1e-9
+    # starts on the left, goals on the right in reversed order: paths cross; displacement L per axis stays inside what
+    # |v| <= 2 allows within the horizon (rest-to-rest peak velocity 1.5 d / T), R shrinks with L so starts are apart
+    L = min(8.0, 0.4 * T)
+    R = min(0.8, 0.6 * L / max(N, 2))
+    ys = np.linspace(6.0 - L / 2, 6.0 + L / 2, N) if N > 1 else np.array([6.0])
+    p0 = np.stack([np.full(N, 2.0) + rng.uniform(-0.02, 0.02, N), ys], axis=1)
+    pf = np.stack([np.full(N, 2.0 + L) + rng.uniform(-0.02, 0.02, N), ys[::-1]], axis=1)
+    traj, recs, _ = _solve(p0, pf, T, h, R, space)
+    assert traj["positions"].shape == (1, N, K, 2)
+    r = recs[0]
+    tc, rc = BatchSolver(N, T, h, R, space).solve(p0[None], pf[None])
+    z = np.zeros((N, 2))
+    assert r["status"] == rc[0]["status"] == 0
+    assert r["initial_feasible"] == rc[0]["initial_feasible"]
+    dyn = scp_oracle.dynamics_residual(traj["accelerations"][0], p0, z, pf, z, h, space, positions=traj["positions"][0])
+    assert dyn <= DYN_TOL
+    if N > 1:
+        assert abs(r["min_separation"] - scp_oracle.min_separation(traj["positions"][0])) <= 1e-12
+    if r["qp_unsolved"] == 0 and rc[0]["qp_unsolved"] == 0 and r["scp_iterations"] == rc[0]["scp_iterations"]:
+        perr = np.linalg.norm(traj["positions"][0] - tc["positions"][0]) / np.linalg.norm(tc["positions"][0])
+        assert perr <= POS_TOL, perr
+        assert (r["min_separation"] >= R - 0.01) == (rc[0]["min_separation"] >= R - 0.01)
+    else:
+        assert N > 1          # a single agent has nothing that could stay unsolved
+
+
+def test_stream_failure_paths(torch_cuda):
+    """scp.py:846-865 demo inputs (first avoidance QP infeasible: warning + loop continues, scp.py:446-449) and two
+    agents that start closer than R (k = 0 rows infeasible): no exception, no hang, the record says what happened."""
+    p0 = np.array([[-2.0, -2], [0, -2], [2, -2]])
+    pf = np.array([[2.0, 2], [0, 2], [-2, 2]])
+    traj, recs, _ = _solve(p0, pf, 3.0, 0.2, 0.5, [-5, -5, 500, 200], max_admm_iter=3000)
+    r = recs[0]
+    assert r["status"] == 0 and not r["initial_feasible"]
+    assert r["first_violation"][1:] == (0, 1) and r["first_violation_dist"] < 0.49
+    assert r["qp_unsolved"] >= 1 and r["scp_iterations"] >= 1
+    assert np.isfinite(traj["accelerations"]).all() and r["min_separation"] < 0.5 - 0.01
+    p0 = np.array([[5.0, 5.0], [5.3, 5.0]])
+    pf = np.array([[15.0, 5.0], [15.0, 8.0]])
+    _, recs, _ = _solve(p0, pf, 10.0, 0.2, 0.8, [0, 0, 20, 20], max_admm_iter=2000)
+    assert recs[0]["status"] == 2 and recs[0]["first_violation"] == (0, 0, 1)
+
+
 def test_stream_agent_sharded_matches_single_gpu(torch_cuda):
     """World-size-2 agent-sharded solve (NCCL all-gather of positions per ADMM iteration) == the one-GPU solve."""
     if torch_cuda.cuda.device_count() < 2:
