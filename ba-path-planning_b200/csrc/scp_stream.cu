@@ -540,7 +540,7 @@ __device__ __forceinline__ void p2p_wait(const Dev& d) {
 
 // BOX = 0: no box-row class is carried by this scenario's ADMM (the usual state with lazy rows) -- all box code
 // compiles away and only x and the positions move through memory.
-template <int EPL, int CHK, int BOX>
+template <int EPL, int CHK, int BOX, int VEC>
 __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc, int cur, double* sm) {
   const int b = blockIdx.y;
   const int K = d.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, npair = blockDim.x >> 6;
@@ -548,7 +548,7 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   const int ax = warp & 1;                                    // two warps per agent: one per axis
   double* Nm = sm;
   double* myrhs = sm + (size_t)K * K + 4 + (size_t)warp * (K + (K & 1));   // 4 doubles of padding behind the operator
-  const bool vec = (K & 1) == 0;
+  constexpr bool vec = VEC != 0;      // K even: rows are 16-byte aligned and move as double2 (compile time: no dual code paths)
   if (threadIdx.x < 4) sm[(size_t)K * K + threadIdx.x] = 0.0;
   {  // operator -> shared memory, asynchronously (cp.async 16 B) when rows are 16-byte aligned
     const double* src = d.Nmat + (size_t)b * K * K;
@@ -864,8 +864,9 @@ __global__ void __launch_bounds__(IT_THREADS, 2) k_iter(const __grid_constant__ 
   const State& S = d.st[blockIdx.y];
   if (S.phase >= 2) return;
   if (d.a_lo + (int)blockIdx.x * apc >= d.a_hi) return;
-  if (S.on_mask == 0) iter_body<EPL, CHK, 0>(d, S, apc, cur, sm);
-  else iter_body<EPL, CHK, 1>(d, S, apc, cur, sm);
+  const bool even = (d.K & 1) == 0;
+  if (S.on_mask == 0) { if (even) iter_body<EPL, CHK, 0, 1>(d, S, apc, cur, sm); else iter_body<EPL, CHK, 0, 0>(d, S, apc, cur, sm); }
+  else { if (even) iter_body<EPL, CHK, 1, 1>(d, S, apc, cur, sm); else iter_body<EPL, CHK, 1, 0>(d, S, apc, cur, sm); }
 }
 
 // the kernels after a check iteration read every agent's positions: wait until all peers have published it
@@ -1492,6 +1493,7 @@ void scp_b200_stream_default_problem(scp_b200_problem* prob, int n_agents, doubl
   const double kr = 50.0 / (double)(prob->n_steps > 1 ? prob->n_steps : 1);
   prob->rho0 = fmin(1.0, fmax(0.1, kr * kr));
   prob->stall_window = 1000;
+  prob->check_every = 50;      // a check period costs ~15 small launches: fewer of them (a subproblem runs 10^3..10^4 iterations)
 }
 
 int scp_b200_nccl_unique_id(void* id128) {
