@@ -550,11 +550,23 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   double* myrhs = sm + (size_t)K * K + 4 + (size_t)warp * (K + (K & 1));   // 4 doubles of padding behind the operator
   constexpr bool vec = VEC != 0;      // K even: rows are 16-byte aligned and move as double2 (compile time: no dual code paths)
   if (threadIdx.x < 4) sm[(size_t)K * K + threadIdx.x] = 0.0;
-  {  // operator -> shared memory, asynchronously (cp.async 16 B) when rows are 16-byte aligned
+  // operator -> shared memory: ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by thread 0 when
+  // the rows are 16-byte aligned; it lands while the collision rows are walked
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar);
+  {
     const double* src = d.Nmat + (size_t)b * K * K;
     if (vec) {
-      for (int e = threadIdx.x; e < K * K / 2; e += blockDim.x) __pipeline_memcpy_async(Nm + 2 * e, src + 2 * e, 16);
-      __pipeline_commit();
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_a), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)((size_t)K * K * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(Nm)),
+                     "l"(src), "r"(bytes), "r"(mbar_a)
+                     : "memory");
+      }
     } else {
       for (int e = threadIdx.x; e < K * K; e += blockDim.x) Nm[e] = src[e];
     }
@@ -666,8 +678,14 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
       }
     }
     if (!staged) {
-      if (vec) __pipeline_wait_prior(0);
-      __syncthreads();
+      __syncthreads();              // mbarrier initialised (thread 0) / plain staging stores done
+      if (vec) {
+        unsigned ok = 0;
+        do {
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(ok) : "r"(mbar_a), "r"(0u) : "memory");
+        } while (!ok);
+      }
       staged = true;
     }
     if (!live) break;
