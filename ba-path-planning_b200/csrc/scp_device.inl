@@ -1637,6 +1637,9 @@ SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double
 
 // ------------------------------------------------------------------ ADMM
 struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua; };
+// a subproblem whose active set keeps cycling stops asking for the polish after this many failed attempts and ends on
+// the ADMM residual test instead (a few scenarios spent > 50 attempts x 40 rounds: the tail of a batch)
+constexpr int POLISH_MAX_FAILED = 10;
 
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
   AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY;
@@ -1737,7 +1740,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
       const double gate = c.g->pb.polish_first_eps;
       const int settled = (sc == prev_sc && ss == prev_ss) && !(sc == fail_sc && ss == fail_ss);
       prev_sc = sc; prev_ss = ss;
-      if (settled && pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua)) {
+      if (settled && o.polish_attempts < POLISH_MAX_FAILED && pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua)) {
         const long long t0 = SCP_CLOCK();
         const int pol = polish(c, with_collisions, c.g->pb.polish_rounds);
         c.t_polish += SCP_CLOCK() - t0;
@@ -1778,10 +1781,14 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
 
 // One subproblem: a single ADMM run to the final tolerance; the polish is attempted from inside the
 // run whenever the active set has settled, and ends it with the exact minimiser when it certifies.
-SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state) {
+SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state, int cap_hits = 0) {
   const long long t0 = SCP_CLOCK();
   const long long p0 = c.t_polish;
-  AdmmOut a = admm_run(c, with_collisions, keep_state, c.g->pb.eps_abs, c.g->pb.eps_rel, c.g->pb.max_admm_iter);
+  // every subproblem of this scenario that ran into the iteration cap halves the cap of the next ones (floor 500):
+  // from its first unsolved subproblem on the scenario's iterates are solver dependent anyway (scp.py:446-449)
+  int cap = c.g->pb.max_admm_iter >> (cap_hits < 3 ? cap_hits : 3);
+  if (cap < 500) cap = c.g->pb.max_admm_iter < 500 ? c.g->pb.max_admm_iter : 500;
+  AdmmOut a = admm_run(c, with_collisions, keep_state, c.g->pb.eps_abs, c.g->pb.eps_rel, cap);
   c.t_admm += (SCP_CLOCK() - t0) - (c.t_polish - p0);
   return a;
 }
@@ -1885,7 +1892,7 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
       build_candidates(c);
       if (c.copies > r.max_copies) r.max_copies = c.copies;
       if (!have_state || c.copies != old_copies) factor_operator(c);
-      a = solve_qp(c, 1, have_state || keep);          // QP #t, scp.py:155
+      a = solve_qp(c, 1, have_state || keep, r.qp_unsolved - r.qp_infeasible);          // QP #t, scp.py:155
       have_state = 1;
       r.admm_iterations += a.iters;
       r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;
