@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(512) k_factor(const __grid_constant__ Dev d) {
 }
 
 // ---------------------------------------------------------------------------------- agent-axis kernel
-// (MODE 0/1 are the first, two-kernel form of the iteration -- k_axis + k_collide -- kept for reference and for
+// (MODE 0/1 are the agent-axis half of the first, two-kernel form of the iteration, kept for reference and for
 // debugging against k_iter; only MODE 2 is launched.)
 // One warp per (scenario, agent-axis): lanes hold the steps k = lane + 32 e.  MODE 0: one ADMM iteration of the
 // box rows and the x-update (scp_device.inl admm_iter_fused, state streamed from HBM/L2 instead of shared memory);
@@ -973,49 +973,6 @@ __global__ void k_local_sums(const __grid_constant__ Dev d) {
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
   if (lane == 0) { double* sl = d.slab + (size_t)b * NRED; sl[R_DN] = s0; sl[R_PN] = s1; sl[R_OBJ] = s2; }
-}
-
-// ---------------------------------------------------------------------------------- collision rows
-// One thread per (scenario, own agent i, step k >= 1), k fastest: walks the candidate rows of (k, i), updates the
-// row multipliers (both owners keep identical copies) and sums the force on p_i[k]  (scp_device.inl collision_rows).
-template <int CHK>
-__global__ void __launch_bounds__(256) k_collide(const __grid_constant__ Dev d) {
-  const int b = blockIdx.y;
-  const State& S = d.st[b];
-  if (S.phase != 1) return;
-  const int K = d.K, Nown = d.a_hi - d.a_lo;
-  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
-  double worst = 0.0;
-  if (tl < Nown * K) {
-    const int il = tl / K, k = tl - il * K, i = d.a_lo + il;
-    if (k >= 1) {
-      const size_t T = (size_t)d.B * Nown * K, t = ((size_t)b * Nown + il) * K + k;
-      const double* Pb = d.P + (size_t)b * d.Qs * K;
-      const double pix = Pb[(size_t)(2 * i) * K + k], piy = Pb[(size_t)(2 * i + 1) * K + k];
-      const double rc = S.rho * d.rc[k - 1];
-      const int n = d.cnt[t];
-      double fx = 0, fy = 0, yx = 0, yy = 0;
-      for (int s = 0; s < n; ++s) {
-        const size_t o = (size_t)s * T + t;
-        const int j = d.cj[o];
-        const double ex = d.cex[o], ey = d.cey[o];
-        const double g = ex * (pix - Pb[(size_t)(2 * j) * K + k]) + ey * (piy - Pb[(size_t)(2 * j + 1) * K + k]);
-        const double l0 = d.lam[o];
-        const double l1 = fmax(0.0, l0 + 0.5 * rc * (d.cb[o] - g));
-        d.lam[o] = l1;
-        const double f = 2.0 * l1 - l0;
-        fx += f * ex; fy += f * ey;
-        if (CHK) { yx += l1 * ex; yy += l1 * ey; worst = fmax(worst, fabs(l1 - l0) / rc); }
-      }
-      const size_t r0 = ((size_t)b * d.Qs + 2 * i) * K + k;
-      d.F[r0] = fx; d.F[r0 + K] = fy;
-      if (CHK) { d.FY[r0] = yx; d.FY[r0 + K] = yy; }
-    }
-  }
-  if (CHK) {
-    worst = warp_max_nan(fabs(worst));
-    if ((threadIdx.x & 31) == 0 && worst > 0.0) atomic_max_pos(d.slab + (size_t)b * NRED + R_PRICOL, worst);
-  }
 }
 
 // ---------------------------------------------------------------------------------- snapshot / candidates
