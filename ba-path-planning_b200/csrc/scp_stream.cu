@@ -1342,24 +1342,25 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
-NcclApi* nccl_api() {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried) return api.handle ? &api : nullptr;
-  tried = true;
+NcclApi load_nccl_api() {
+  NcclApi api;
   const char* env = getenv("SCP_B200_NCCL_LIB");
   void* h = env ? dlopen(env, RTLD_NOW | RTLD_GLOBAL) : nullptr;
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);   // the copy PyTorch already loaded
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) return nullptr;
+  if (!h) return api;
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
   api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-  if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) return nullptr;
-  api.handle = h;
-  return &api;
+  if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy) api.handle = h;
+  return api;
+}
+
+NcclApi* nccl_api() {
+  static NcclApi api = load_nccl_api();      // initialised once, thread safe (C++11 magic static)
+  return api.handle ? &api : nullptr;
 }
 
 }  // namespace ss
