@@ -71,3 +71,38 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
                 assert "scp_emu" not in src
+
+
+def test_stream_default_problem_and_engine_rule():
+    """Host-only pieces of the streaming solver: its default settings (fixed rho scaled with the horizon, relaxation,
+    lazy rows) and the rule that sends single large scenarios to it."""
+    from path_planning.solvers.scp import use_stream_engine
+
+    p = _capi.default_problem(25, 10.0, 0.2, 0.8, [0, 0, 20, 20], stream=True)          # K = 50
+    assert (p.n_agents, p.n_steps, p.polish, p.adapt_every, p.relax_pct, p.lazy_rows) == (25, 50, 0, 0, 160, 1)
+    assert (p.eps_abs, p.eps_rel, p.max_admm_iter, p.check_every, p.stall_window) == (1e-4, 1e-4, 20000, 50, 1000)
+    assert p.rho0 == 1.0 and p.momentum_pct == 0 and p.warm_duals == 0
+    assert _capi.default_problem(200, 20.0, 0.2, 0.8, stream=True).rho0 == pytest.approx(0.25)    # K = 100
+    assert _capi.default_problem(10, 100.0, 0.2, 0.8, stream=True).rho0 == pytest.approx(0.1)     # K = 500: clamped
+    # the one-CTA defaults are untouched by the streaming ones
+    q = _capi.default_problem(25, 10.0, 0.2, 0.8)
+    assert (q.polish, q.adapt_every, q.relax_pct, q.max_admm_iter, q.check_every) == (1, 100, 0, 5000, 25)
+    # engine rule: one (or a few) large scenarios with K <= 128 -> streaming; batches, K = 500 and small ones -> one CTA
+    assert use_stream_engine("auto", 200, 100) and use_stream_engine("auto", 1000, 100, 1)
+    assert not use_stream_engine("auto", 200, 100, 1024) and not use_stream_engine("auto", 10, 500)
+    assert not use_stream_engine("auto", 25, 50) and use_stream_engine("stream", 5, 50) and not use_stream_engine("cta", 1000, 100)
+
+
+def test_stream_create_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call: bad sizes are reported through the error string."""
+    lib = _capi.load()
+    p = _capi.default_problem(5, 10.0, 0.2, 0.8, stream=True)
+    h = C.c_void_p()
+    p.n_steps = 200
+    assert lib.scp_b200_stream_create(C.byref(p), 1, 16, 0, 1, None, C.byref(h)) != 0
+    assert b"n_steps" in lib.scp_b200_last_error()
+    p.n_steps = 50
+    assert lib.scp_b200_stream_create(C.byref(p), 2, 16, 0, 2, None, C.byref(h)) != 0      # sharding solves ONE scenario
+    assert b"ONE scenario" in lib.scp_b200_last_error()
+    assert lib.scp_b200_stream_create(C.byref(p), 1, 16, 3, 2, None, C.byref(h)) != 0      # rank outside world
+    assert h.value is None
