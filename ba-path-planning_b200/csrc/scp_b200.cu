@@ -403,7 +403,9 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   double* ws_d = (double*)(base + HEADER_BYTES);
   int* ws_i = (int*)(base + HEADER_BYTES + g.L.n_double * sizeof(double) * (size_t)slots);
   CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
-  const int resumable = ((long long)B * (prob->max_scp_iter + 2) <= (long long)QUEUE_CAP) ? 1 : 0;
+  // warm_duals keeps the multipliers of the previous subproblem in the slot scratch: a re-queued scenario may resume in
+  // another slot, so that option runs every scenario start to finish in one slot
+  const int resumable = (!prob->warm_duals && (long long)B * (prob->max_scp_iter + 2) <= (long long)QUEUE_CAP) ? 1 : 0;
   if (resumable) CUDA_OK(cudaMemsetAsync(queue, 0xFF, (size_t)B * (prob->max_scp_iter + 2) * sizeof(int), st));
   int hot_mask = 0;
   const size_t nm = nmat_smem_bytes(K);
@@ -431,14 +433,16 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
 }
 
 namespace {
-std::mutex g_cache_mu;
-struct HostCache {      // device buffers reused across scp_b200_solve_batch_host calls
-  int device = -1;
+constexpr int MAX_DEVICES = 64;
+struct HostCache {      // device buffers reused across scp_b200_solve_batch_host calls, one set per device
+  std::mutex mu;        // held for the whole call: calls on ONE device serialise, calls on different devices do not
+  bool init = false;
   void* tables = nullptr; size_t tables_bytes = 0; scp_b200_problem tables_for{};
   void* ws = nullptr; size_t ws_bytes = 0;
   void* io = nullptr; size_t io_bytes = 0;
   cudaStream_t stream = nullptr;
-} g_cache;
+};
+HostCache g_cache[MAX_DEVICES];
 }  // namespace
 
 int scp_b200_solve_batch_host(const scp_b200_problem* prob, int B, const double* h_p0, const double* h_v0,
@@ -446,13 +450,13 @@ int scp_b200_solve_batch_host(const scp_b200_problem* prob, int B, const double*
                               double* h_vel, scp_b200_record* h_records, int device) {
   if (int rc = validate(prob)) return rc;
   if (B <= 0) return 0;
-  std::lock_guard<std::mutex> lock(g_cache_mu);
+  if (device < 0 || device >= MAX_DEVICES) return fail(1, "device index out of range");
+  HostCache& hc = g_cache[device];
+  std::lock_guard<std::mutex> lock(hc.mu);
   CUDA_OK(cudaSetDevice(device));
-  HostCache& hc = g_cache;
-  if (hc.device != device) {
-    hc = HostCache{};   // buffers of another device are simply dropped (process lifetime)
-    hc.device = device;
+  if (!hc.init) {
     CUDA_OK(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
+    hc.init = true;
   }
   const int N = prob->n_agents, K = prob->n_steps;
   const size_t tb = scp_b200_tables_bytes(prob);

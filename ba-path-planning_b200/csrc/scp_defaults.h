@@ -32,5 +32,8 @@ static inline void scp_fill_default_problem(scp_b200_problem* p, int n_agents, d
   p->team_mode = 0;
   p->lazy_rows = 1;
   p->momentum_pct = 0;
+  p->max_admm_iter_qp0 = 0;
+  p->cap_halving = 1;
+  p->polish_max_failed = 10;
 }
 #endif

@@ -43,6 +43,7 @@
 #include "../../include/scp_b200.h"
 
 #ifdef SCP_EMU
+#define SCP_NANOS() 0LL
 #define SCP_CLOCK() 0LL
 #define SCP_DEV inline
 #define SCP_PHASE(c) for (int tid = 0; tid < (c).nthreads; ++tid)
@@ -51,6 +52,7 @@
 #define SCP_FMIN(a, b) ((a) < (b) ? (a) : (b))
 #else
 #define SCP_CLOCK() clock64()
+#define SCP_NANOS() scp_globaltimer()
 #define SCP_DEV __device__ __forceinline__
 #define SCP_PHASE(c) for (int tid = (c).tid0 + threadIdx.x, _once = 1; _once; _once = 0)
 #define SCP_SYNC(c) scp_team_sync((c).team)
@@ -60,6 +62,11 @@
 
 #ifndef SCP_EMU
 #include <cooperative_groups.h>
+__device__ __forceinline__ long long scp_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
 // Barrier of the team that solves one scenario: the CTA (team of 1) or the whole cooperative grid.
 __device__ __forceinline__ void scp_team_sync(int team) {
   if (team > 1) cooperative_groups::this_grid().sync(); else __syncthreads();
@@ -175,31 +182,47 @@ struct Ctx {
 // ------------------------------------------------------------------ reductions
 // Phase-style block reductions over a value every thread contributes.
 // kind 0: max, 1: sum.  Result returned to all threads.
-SCP_DEV double reduce_finish(Ctx& c, int slot, int kind) {
+#ifdef SCP_EMU
+#define SCP_REDUCE_FN inline
+#define SCP_PHASE_ARGS(nt, tid0_) for (int tid = 0; tid < (nt); ++tid)
+#define SCP_SYNC_ARGS(team_) ((void)0)
+#else
+#define SCP_REDUCE_FN __device__ __noinline__
+#define SCP_PHASE_ARGS(nt, tid0_) for (int tid = (tid0_) + threadIdx.x, _once = 1; _once; _once = 0)
+#define SCP_SYNC_ARGS(team_) scp_team_sync(team_)
+#endif
+// A real (non-inlined) function: it has ~50 call sites and takes only scalars, so nothing of the caller's context is
+// forced into memory.
+template <int kind>
+SCP_REDUCE_FN double reduce_finish_impl(double* sh, int rs, int nthreads, int team, int tid0, int slot) {
   // every team thread has written red[tid]; two strided levels (<= 1024, then 32), result to all threads
-  double* red = c.sh + (size_t)slot * c.rs;
-  double* aux = c.sh + (size_t)4 * c.rs + 16;          // 1024 + 32
-  const int n1 = c.nthreads < 1024 ? c.nthreads : 1024;
-  SCP_PHASE(c) {
+  double* red = sh + (size_t)slot * rs;
+  double* aux = sh + (size_t)4 * rs + 16;          // 1024 + 32
+  const int n1 = nthreads < 1024 ? nthreads : 1024;
+  SCP_PHASE_ARGS(nthreads, tid0) {
     if (tid < n1) {
       double a = kind ? 0.0 : -INFINITY;
-      for (int e = tid; e < c.nthreads; e += n1) a = kind ? a + red[e] : SCP_FMAX(a, red[e]);
+      for (int e = tid; e < nthreads; e += n1) a = kind ? a + red[e] : SCP_FMAX(a, red[e]);
       aux[tid] = a;
     }
   }
-  SCP_SYNC(c);
-  SCP_PHASE(c) {
+  SCP_SYNC_ARGS(team);
+  SCP_PHASE_ARGS(nthreads, tid0) {
     if (tid < 32) {
       double a = kind ? 0.0 : -INFINITY;
       for (int e = tid; e < n1; e += 32) a = kind ? a + aux[e] : SCP_FMAX(a, aux[e]);
       aux[1024 + tid] = a;
     }
   }
-  SCP_SYNC(c);
+  SCP_SYNC_ARGS(team);
   double r = kind ? 0.0 : -INFINITY;
   for (int e = 0; e < 32; ++e) r = kind ? r + aux[1024 + e] : SCP_FMAX(r, aux[1024 + e]);
-  SCP_SYNC(c);
+  SCP_SYNC_ARGS(team);
   return r;
+}
+SCP_DEV double reduce_finish(Ctx& c, int slot, int kind) {
+  return kind ? reduce_finish_impl<1>(c.sh, c.rs, c.nthreads, c.team, c.tid0, slot)
+              : reduce_finish_impl<0>(c.sh, c.rs, c.nthreads, c.team, c.tid0, slot);
 }
 
 SCP_DEV double clampd(double v, double lo, double hi) { return SCP_FMIN(SCP_FMAX(v, lo), hi); }
@@ -1142,39 +1165,51 @@ SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_
   SCP_SYNC(c);
   if (nchg > chg_cap) nchg = chg_cap;
   for (int ci = 0; ci < nchg; ++ci) {
+    // one row at a time: [drop the row's old entry] then [add its new one]; a single call site each for the two
+    // O(n^2) updates keeps one copy of them in the kernel
     const int id = chg[ci];
-    if (id < 4 * QK) {
-      const int m = pmark[id], nm = pdec[id];
-      if (m != 0) { n = polish_drop(c, ppos[id], n); SCP_PHASE(c) { if (tid == 0) ppos[id] = -1; } SCP_SYNC(c); }
-      if (nm != 0) {
-        if (n >= c.g->L.pcap) return -1;
-        SCP_PHASE(c) { if (tid == 0) { polish_fill_dyn(c, n, id / QK, id % QK, nm); pid[n] = id; ppos[id] = n; } }
-        SCP_SYNC(c);
-        if (!polish_add(c, g, n)) return -1;
-        ++n;
-      }
-      SCP_PHASE(c) { if (tid == 0) pmark[id] = nm; }
-      SCP_SYNC(c);
+    const int is_col = id >= 4 * QK;
+    const int sidx = is_col ? id - 4 * QK : 0;
+    int m, nm, do_add, drop_pos = -1, ck = 0, ci_ = 0, cjj = 0;
+    if (!is_col) {
+      m = pmark[id]; nm = pdec[id];
+      if (m != 0) drop_pos = ppos[id];
+      do_add = nm != 0;
     } else {
-      const int sidx = id - 4 * QK;
-      const int m = pcmark[sidx], nm = pcdec[sidx];
-      const int t = pcown[sidx], k = t / N, i = t - k * N, j = cj[sidx];
-      if (m != 0) { n = polish_drop(c, pcpos[sidx], n); SCP_PHASE(c) { if (tid == 0) pcpos[sidx] = -1; } SCP_SYNC(c); }
-      else {
-        if (n >= c.g->L.pcap) return -1;
-        SCP_PHASE(c) { if (tid == 0) { polish_fill_col(c, n, sidx, k, i); pid[n] = id; pcpos[sidx] = n; } }
-        SCP_SYNC(c);
-        if (!polish_add(c, g, n)) return -1;
-        ++n;
-      }
+      m = pcmark[sidx]; nm = pcdec[sidx];
+      const int t = pcown[sidx];
+      ck = t / N; ci_ = t - ck * N; cjj = cj[sidx];
+      if (m != 0) drop_pos = pcpos[sidx];
+      do_add = (m == 0);
+    }
+    if (drop_pos >= 0) {
+      n = polish_drop(c, drop_pos, n);
+      SCP_PHASE(c) { if (tid == 0) { if (is_col) pcpos[sidx] = -1; else ppos[id] = -1; } }
+      SCP_SYNC(c);
+    }
+    if (do_add) {
+      if (n >= c.g->L.pcap) return -1;
       SCP_PHASE(c) {
         if (tid == 0) {
-          pcmark[sidx] = nm;
-          for (int s2 = coff[k * N + j]; s2 < coff[k * N + j + 1]; ++s2) if (cj[s2] == i) pcmark[s2] = nm;   // mirror entry
+          if (is_col) { polish_fill_col(c, n, sidx, ck, ci_); pcpos[sidx] = n; }
+          else { polish_fill_dyn(c, n, id / QK, id % QK, nm); ppos[id] = n; }
+          pid[n] = id;
         }
       }
       SCP_SYNC(c);
+      if (!polish_add(c, g, n)) return -1;
+      ++n;
     }
+    SCP_PHASE(c) {
+      if (tid == 0) {
+        if (!is_col) pmark[id] = nm;
+        else {
+          pcmark[sidx] = nm;
+          for (int s2 = coff[ck * N + cjj]; s2 < coff[ck * N + cjj + 1]; ++s2) if (cj[s2] == ci_) pcmark[s2] = nm;   // mirror entry
+        }
+      }
+    }
+    SCP_SYNC(c);
   }
   return n;
 }
@@ -1291,12 +1326,18 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
       }
   }
   SCP_SYNC(c);
-  int n = polish_apply(c, g, fresh ? 0 : c.pol_n, use_col, 0.0, 0.0);
-  c.t_pbuild += SCP_CLOCK() - tq;
-  c.pol_use_col = use_col; c.pol_n = n; c.pol_valid = n >= 0; c.pol_col_stale = 0;
-  if (n < 0) return 0;
-
-  for (int round = 0; round < max_rounds; ++round) {
+  int n = fresh ? 0 : c.pol_n;
+  double ta = 0.0, td = 0.0;               // score thresholds of the pending decisions (0: apply all of them)
+  for (int round = 0;; ++round) {
+    // pending mark changes -> list / inverse: the initial guess before round 0, the decisions of round-1 afterwards
+    // (ONE call site: polish_apply and the O(n^2) updates it calls exist once in the kernel)
+    if (round > 0) tq = SCP_CLOCK();
+    n = polish_apply(c, g, n, use_col, ta, td);
+    if (round == 0) { c.t_pbuild += SCP_CLOCK() - tq; c.pol_use_col = use_col; c.pol_col_stale = 0; }
+    else c.t_papply += SCP_CLOCK() - tq;
+    c.pol_n = n; c.pol_valid = n >= 0;
+    if (n < 0) return 0;
+    if (round >= max_rounds) break;
     c.polish_rounds++;
     tq = SCP_CLOCK();
     if (n > 0 && !polish_solve(c, n)) { c.pol_valid = 0; return 0; }
@@ -1450,16 +1491,12 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
 #endif
     c.t_peval += SCP_CLOCK() - tq;
     if (broken > 0.0) return 0;             // active rows not met as equalities: inconsistent (infeasible) set
-    if (changes > 0.0) {
-      // apply the decisions: all of them in the first rounds (primal-dual active set step); afterwards only the
-      // worst violated row and the worst wrong-sign multiplier per round, which breaks the cycles the full step can enter
+    {
+      // the decisions are applied at the top of the next round: all of them in the first rounds (primal-dual active
+      // set step); afterwards only the worst violated row and the worst wrong-sign multiplier per round, which
+      // breaks the cycles the full step can enter
       const int careful = round >= full_rounds;
-      const double ta = careful ? madd * (1.0 - 1e-12) : 0.0, td = careful ? mdrop * (1.0 - 1e-12) : 0.0;
-      tq = SCP_CLOCK();
-      n = polish_apply(c, g, n, use_col, ta, td);
-      c.t_papply += SCP_CLOCK() - tq;
-      c.pol_n = n; c.pol_valid = n >= 0;
-      if (n < 0) return 0;
+      ta = careful ? madd * (1.0 - 1e-12) : 0.0; td = careful ? mdrop * (1.0 - 1e-12) : 0.0;
     }
 #ifdef SCP_EMU_DEBUG
     if (changes == 0.0) fprintf(stderr, "  POLISH OK after %d rounds n=%d\n", round + 1, n);
@@ -1637,119 +1674,120 @@ SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double
 
 // ------------------------------------------------------------------ ADMM
 struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua; };
-// a subproblem whose active set keeps cycling stops asking for the polish after this many failed attempts and ends on
-// the ADMM residual test instead (a few scenarios spent > 50 attempts x 40 rounds: the tail of a batch)
-constexpr int POLISH_MAX_FAILED = 10;
+// a subproblem whose active set keeps cycling stops asking for the polish after pb.polish_max_failed failed attempts and
+// ends on the ADMM residual test instead (a few scenarios spent > 50 attempts x 40 rounds: the tail of a batch)
 
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
   AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY;
   const int K = c.K;
   double* red = c.sh;
   double* x = c.a_x;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
+  double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
+  double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *off = c.wd + c.g->L.off;
+  const double ih = 1.0 / c.g->pb.time_step;
   if (!keep_state) forward_rows(c, 0);
-  if (c.g->pb.polish && c.g->pb.polish_first) {
-    // try the active set the state already implies (previous subproblem's multipliers with warm duals,
-    // nothing otherwise) before iterating at all
-    const long long t0 = SCP_CLOCK();
-    const int pol = polish(c, with_collisions, c.g->pb.polish_first);
-    c.t_polish += SCP_CLOCK() - t0;
-    o.polish_attempts++;
-    if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; return o; }
-  }
   const int check = c.g->pb.check_every;
   double prev_sc = -1.0, prev_ss = -1.0, fail_sc = -2.0, fail_ss = -2.0;
   int it_mark = 0; double pri_mark = INFINITY;
-  for (int it = 1; it <= maxit; ++it) {
-    const int chk = (it % check == 0) || it == maxit;
+  // polish_first: "iteration 0" is a polish attempt on the active set the state already implies (previous
+  // subproblem's multipliers with warm duals, nothing otherwise) before iterating at all.  It shares the ONE polish
+  // call site below, so that the polish (and everything it inlines) exists once in the kernel.
+  const int pre_polish = (c.g->pb.polish && c.g->pb.polish_first) ? 1 : 0;
+  for (int it = pre_polish ? 0 : 1; it <= maxit; ++it) {
+    int want_polish = 0, chk = 0;          // rounds of the polish attempt this pass makes (0: none); residual check
+    double sc = 0.0, ss = 0.0, pri = 0.0, npri = 0.0, dua = 0.0, ndua = 0.0;
+    if (it == 0) want_polish = c.g->pb.polish_first;
+    else {
+      chk = (it % check == 0) || it == maxit;
 #ifndef SCP_EMU
-    if (!chk && c.fused_epl > 0) {
-      admm_iter_fused<2>(c, c.fused_rows);
-      __syncthreads();
-    } else
+      if (!chk && c.fused_epl > 0) {
+        admm_iter_fused<2>(c, c.fused_rows);
+        __syncthreads();
+      } else
 #endif
-    {
-      transpose_rows(c, 0);
-      x_update(c, chk);
-      forward_rows(c, 1, chk);
-    }
-    double pri_col = 0.0;
-    if (with_collisions && c.ncand > 0) {
-      collision_rows(c, chk);
-      if (chk) pri_col = reduce_finish(c, 0, 0);
-    }
-    o.iters = it;
-    if (!chk) continue;
-    // ---- residuals in reference units (OSQP termination test, unscaled)
-    const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
-    const double lo[2] = {c.g->pb.space[0], c.g->pb.space[1]}, hi[2] = {c.g->pb.space[2], c.g->pb.space[3]};
-    double *vj = c.a_vj, *va = c.a_va, *vv = c.a_vv, *vp = c.a_vp;
-    double *posrow = c.wd + c.g->L.posrow, *velrow = c.wd + c.g->L.velrow, *off = c.wd + c.g->L.off;
-    const double ih = 1.0 / c.g->pb.time_step;
-    SCP_PHASE(c) {
-      double pr = 0.0, nr = 0.0;
-      for (int e = tid; e < c.Q * K; e += c.nthreads) {
-        int q = e / K, k = e - q * K;
-        double ax = x[e];
-        pr = SCP_FMAX(pr, fabs(ax - clampd(va[e], -al, al)));
-        nr = SCP_FMAX(nr, fabs(ax));
-        if (k < K - 1) {
-          double aj = (x[e + 1] - ax) * ih;
-          pr = SCP_FMAX(pr, fabs(aj - clampd(vj[e], -jl, jl)));
-          double v0q = c.v0[q];
-          pr = SCP_FMAX(pr, fabs(velrow[e] - clampd(vv[e], -vl - v0q, vl - v0q)));
-          int a2 = q & 1;
-          pr = SCP_FMAX(pr, fabs(posrow[e] - clampd(vp[e], lo[a2] - off[e], hi[a2] - off[e])));
-          nr = SCP_FMAX(nr, SCP_FMAX(fabs(aj), SCP_FMAX(fabs(velrow[e]), fabs(posrow[e]))));
+      {
+        transpose_rows(c, 0);
+        x_update(c, chk);
+        forward_rows(c, 1, chk);
+      }
+      double pri_col = 0.0;
+      if (with_collisions && c.ncand > 0) {
+        collision_rows(c, chk);
+        if (chk) pri_col = reduce_finish(c, 0, 0);
+      }
+      o.iters = it;
+      if (chk) {
+        // ---- residuals in reference units (OSQP termination test, unscaled)
+        SCP_PHASE(c) {
+          double pr = 0.0, nr = 0.0;
+          for (int e = tid; e < c.Q * K; e += c.nthreads) {
+            int q = e / K, k = e - q * K;
+            double ax = x[e];
+            pr = SCP_FMAX(pr, fabs(ax - clampd(va[e], -al, al)));
+            nr = SCP_FMAX(nr, fabs(ax));
+            if (k < K - 1) {
+              double aj = (x[e + 1] - ax) * ih;
+              pr = SCP_FMAX(pr, fabs(aj - clampd(vj[e], -jl, jl)));
+              double v0q = c.v0[q];
+              pr = SCP_FMAX(pr, fabs(velrow[e] - clampd(vv[e], -vl - v0q, vl - v0q)));
+              int a2 = q & 1;
+              pr = SCP_FMAX(pr, fabs(posrow[e] - clampd(vp[e], lo[a2] - off[e], hi[a2] - off[e])));
+              nr = SCP_FMAX(nr, SCP_FMAX(fabs(aj), SCP_FMAX(fabs(velrow[e]), fabs(posrow[e]))));
+            }
+          }
+          red[tid] = pr; red[c.rs + tid] = nr;
+        }
+        SCP_SYNC(c);
+        pri = reduce_finish(c, 0, 0);
+        npri = reduce_finish(c, 1, 0);
+        pri = SCP_FMAX(pri, pri_col);
+        transpose_rows(c, 1);      // rhs <- 2x + A'y + C'mu
+        const double* dres = c.a_rhs;
+        SCP_PHASE(c) {
+          double du = 0.0, nd = 0.0;
+          for (int e = tid; e < c.Q * K; e += c.nthreads) {
+            du = SCP_FMAX(du, fabs(dres[e]));
+            nd = SCP_FMAX(nd, SCP_FMAX(fabs(2.0 * x[e]), fabs(dres[e] - 2.0 * x[e])));
+          }
+          red[tid] = du; red[c.rs + tid] = nd;
+        }
+        SCP_SYNC(c);
+        dua = reduce_finish(c, 0, 0);
+        ndua = reduce_finish(c, 1, 0);
+        o.pri = pri; o.dua = dua;
+        if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
+        if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
+        if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
+        // stalled: the primal residual is still far from feasibility and has not dropped by 20 % over the last
+        // `stall_window` iterations -- the signature of an infeasible subproblem long before the certificate's
+        // direction test converges.  The iterate is kept, as for an iteration-limit exit (scp.py:446-449).
+        if (c.g->pb.stall_window > 0 && it - it_mark >= c.g->pb.stall_window) {
+          if (pri > 1e-3 * (1.0 + npri) && pri > 0.8 * pri_mark) { o.infeasible = 2; break; }
+          it_mark = it; pri_mark = pri;
+        }
+        if (c.g->pb.polish) {
+          // polish when the active set has not changed between two consecutive checks (and differs from the
+          // last set that failed), once the iterate is inside a loose residual gate
+          active_signature(c, with_collisions, &sc, &ss);
+          const double gate = c.g->pb.polish_first_eps;
+          const int settled = (sc == prev_sc && ss == prev_ss) && !(sc == fail_sc && ss == fail_ss);
+          prev_sc = sc; prev_ss = ss;
+          if (settled && o.polish_attempts < c.g->pb.polish_max_failed && pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua))
+            want_polish = c.g->pb.polish_rounds;
         }
       }
-      red[tid] = pr; red[c.rs + tid] = nr;
     }
-    SCP_SYNC(c);
-    double pri = reduce_finish(c, 0, 0);
-    double npri = reduce_finish(c, 1, 0);
-    pri = SCP_FMAX(pri, pri_col);
-    transpose_rows(c, 1);      // rhs <- 2x + A'y + C'mu
-    const double* dres = c.a_rhs;
-    SCP_PHASE(c) {
-      double du = 0.0, nd = 0.0;
-      for (int e = tid; e < c.Q * K; e += c.nthreads) {
-        du = SCP_FMAX(du, fabs(dres[e]));
-        nd = SCP_FMAX(nd, SCP_FMAX(fabs(2.0 * x[e]), fabs(dres[e] - 2.0 * x[e])));
-      }
-      red[tid] = du; red[c.rs + tid] = nd;
+    if (want_polish) {
+      const long long t0 = SCP_CLOCK();
+      const int pol = polish(c, with_collisions, want_polish);
+      c.t_polish += SCP_CLOCK() - t0;
+      o.polish_attempts++;
+      if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; break; }
+      if (it > 0) { fail_sc = sc; fail_ss = ss; }
     }
-    SCP_SYNC(c);
-    double dua = reduce_finish(c, 0, 0);
-    double ndua = reduce_finish(c, 1, 0);
-    o.pri = pri; o.dua = dua;
-    if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
-    if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
-    if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
-    // stalled: the primal residual is still far from feasibility and has not dropped by 20 % over the last
-    // `stall_window` iterations -- the signature of an infeasible subproblem long before the certificate's
-    // direction test converges.  The iterate is kept, as for an iteration-limit exit (scp.py:446-449).
-    if (c.g->pb.stall_window > 0 && it - it_mark >= c.g->pb.stall_window) {
-      if (pri > 1e-3 * (1.0 + npri) && pri > 0.8 * pri_mark) { o.infeasible = 2; break; }
-      it_mark = it; pri_mark = pri;
-    }
-    if (c.g->pb.polish) {
-      // polish when the active set has not changed between two consecutive checks (and differs from the
-      // last set that failed), once the iterate is inside a loose residual gate
-      double sc, ss;
-      active_signature(c, with_collisions, &sc, &ss);
-      const double gate = c.g->pb.polish_first_eps;
-      const int settled = (sc == prev_sc && ss == prev_ss) && !(sc == fail_sc && ss == fail_ss);
-      prev_sc = sc; prev_ss = ss;
-      if (settled && o.polish_attempts < POLISH_MAX_FAILED && pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua)) {
-        const long long t0 = SCP_CLOCK();
-        const int pol = polish(c, with_collisions, c.g->pb.polish_rounds);
-        c.t_polish += SCP_CLOCK() - t0;
-        o.polish_attempts++;
-        if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; break; }
-        fail_sc = sc; fail_ss = ss;
-      }
-    }
-    if (c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
+    if (chk && c.g->pb.adapt_every > 0 && it % c.g->pb.adapt_every == 0 && it < maxit) {
       double est = sqrt((pri / SCP_FMAX(npri, 1e-12)) / SCP_FMAX(dua / SCP_FMAX(ndua, 1e-12), 1e-12));
       if (est > 5.0 || est < 0.2) {
         est = clampd(est, 1e-2, 1e2);
@@ -1786,8 +1824,12 @@ SCP_DEV AdmmOut solve_qp(Ctx& c, int with_collisions, int keep_state, int cap_hi
   const long long p0 = c.t_polish;
   // every subproblem of this scenario that ran into the iteration cap halves the cap of the next ones (floor 500):
   // from its first unsolved subproblem on the scenario's iterates are solver dependent anyway (scp.py:446-449)
-  int cap = c.g->pb.max_admm_iter >> (cap_hits < 3 ? cap_hits : 3);
-  if (cap < 500) cap = c.g->pb.max_admm_iter < 500 ? c.g->pb.max_admm_iter : 500;
+  int cap = c.g->pb.max_admm_iter;
+  if (!with_collisions && c.g->pb.max_admm_iter_qp0 > 0) cap = c.g->pb.max_admm_iter_qp0;   // OSQP default max_iter, scp.py:360
+  if (c.g->pb.cap_halving) {
+    cap >>= (cap_hits < 3 ? cap_hits : 3);
+    if (cap < 500) cap = c.g->pb.max_admm_iter < 500 ? c.g->pb.max_admm_iter : 500;
+  }
   AdmmOut a = admm_run(c, with_collisions, keep_state, c.g->pb.eps_abs, c.g->pb.eps_rel, cap);
   c.t_admm += (SCP_CLOCK() - t0) - (c.t_polish - p0);
   return a;
@@ -1832,80 +1874,90 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
     r.cycles_pbuild = r.cycles_psolve = r.cycles_peval = r.cycles_papply = 0; r.rebuilds = 0; r.max_copies = 0; r.polish_ok = 0;
     r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
     r.first_violation_dist = 0; r.min_separation = INFINITY; r.objective = 0; r.pri_res = r.dua_res = 0;
-    r.cand_row_iters = 0;
+    r.cand_row_iters = 0; r.device_ns = 0;
     for (int e = 0; e < SCP_B200_MAX_SCP_ITER; ++e) r.rel_step[e] = 0.0;
   }
 
   setup_scenario(c);
   c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0; c.pol_col_stale = 0;
   c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
-  const long long t_begin = SCP_CLOCK();
+  const long long t_begin = SCP_CLOCK(), ns_begin = SCP_NANOS();
   double minsep; long long frow; double fdist;
   int feasible = 0, it = 0, converged = 0;
-  if (stage == 0) {
-    factor_operator(c);
-    AdmmOut a0 = solve_qp(c, 0, 0);
-    r.polish_ok += a0.certified; r.polish_attempts += a0.polish_attempts;                       // QP #0, scp.py:138
-    r.admm_iterations += a0.iters; r.pri_res = a0.pri; r.dua_res = a0.dua;
-    if (!a0.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
-    forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
-    gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
-    feasible = frow < 0;
-    r.initial_feasible = feasible;
-    if (!feasible) {
-      long long npairs = (long long)N * (N - 1) / 2;
-      int k = (int)(frow / npairs); long long p = frow - (long long)k * npairs;
-      int i = 0; while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
-      r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = i + 1 + (int)p;
-      r.first_violation_dist = fdist;
-      if (k == 0) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
-    }
-  } else {
+  double* x = c.a_x;
+  double* xprev = c.wd + c.g->L.xprev;
+  double* P = c.a_P;
+  double* Pb = c.wd + c.g->L.Pbar;
+  int qp0 = (stage == 0);                 // the first pass of the loop below is the initial QP (scp.py:138)
+  if (!qp0) {
     // resume: accelerations of the last iterate -> x, positions
-    double* xr = c.a_x;
     SCP_PHASE(c) {
       for (int e = tid; e < c.Q * K; e += c.nthreads) {
         int q = e / K, k = e - q * K;
-        xr[e] = c.acc[((size_t)(q >> 1) * K + k) * 2 + (q & 1)];
+        x[e] = c.acc[((size_t)(q >> 1) * K + k) * 2 + (q & 1)];
       }
     }
     SCP_SYNC(c);
     forward_rows(c, 0);
     it = r.scp_iterations;
   }
-  double* x = c.a_x;
-  double* xprev = c.wd + c.g->L.xprev;
-  double* P = c.a_P;
-  double* Pb = c.wd + c.g->L.Pbar;
-  while (r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
-    SCP_PHASE(c) {
-      for (int e = tid; e < c.Q * K; e += c.nthreads) { Pb[e] = P[e]; xprev[e] = x[e]; }
+  // One loop for QP #0 and the avoidance QPs, so that solve_qp -> admm_run -> polish is inlined at ONE call site
+  // (the fully inlined kernel with two sites was 88 k instructions and took 7 minutes to compile).
+  for (;;) {
+    int warm = 0;
+    if (!qp0) {
+      if (!(r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible)) break;
+      SCP_PHASE(c) {
+        for (int e = tid; e < c.Q * K; e += c.nthreads) { Pb[e] = P[e]; xprev[e] = x[e]; }
+      }
+      SCP_SYNC(c);
+      warm = c.g->pb.warm_duals && it > 0;               // OSQP restarts y = 0 every SCP iteration (scp.py:441-443);
+      mark_near_rows(c, c.g->pb.cand_margin, warm);      // keeping the duals changes the path, not the minimiser
+      if (!warm) c.rho = c.g->pb.rho0;
     }
-    SCP_SYNC(c);
-    AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.infeasible = 0; a.pri = a.dua = 0;
-    const int warm = c.g->pb.warm_duals && it > 0;     // OSQP restarts y = 0 every SCP iteration (scp.py:441-443);
-    mark_near_rows(c, c.g->pb.cand_margin, warm);      // keeping the duals changes the path, not the minimiser
-    if (!warm) c.rho = c.g->pb.rho0;
-    int have_state = 0, keep = warm;
+    AdmmOut a; a.iters = 0; a.solved = 0; a.certified = 0; a.infeasible = 0; a.polish_attempts = 0; a.pri = a.dua = 0;
+    int have_state = 0;
     for (int attempt = 0;; ++attempt) {
-      int old_copies = c.copies;
-      build_candidates(c);
-      if (c.copies > r.max_copies) r.max_copies = c.copies;
-      if (!have_state || c.copies != old_copies) factor_operator(c);
-      a = solve_qp(c, 1, have_state || keep, r.qp_unsolved - r.qp_infeasible);          // QP #t, scp.py:155
+      int need_factor = 1;
+      if (!qp0) {
+        const int old_copies = c.copies;
+        build_candidates(c);
+        if (c.copies > r.max_copies) r.max_copies = c.copies;
+        need_factor = !have_state || c.copies != old_copies;
+      }
+      if (need_factor) factor_operator(c);
+      a = solve_qp(c, !qp0, !qp0 && (have_state || warm), qp0 ? 0 : r.qp_unsolved - r.qp_infeasible);   // QP #0 scp.py:138, QP #t scp.py:155
       have_state = 1;
       r.admm_iterations += a.iters;
+      if (qp0) break;
       r.cand_row_iters += 0.5 * (double)c.ncand * (double)a.iters;
       if (!a.solved) break;                            // unsolved (e.g. infeasible) subproblem: keep x, like scp.py:446-449
       int bad = (c.ncand < N * (N - 1) * (K - 1)) ? verify_rows(c, c.g->pb.verify_tol) : 0;
       if (bad == 0 || attempt >= 20) break;
       r.rebuilds++;
     }
-    if (!a.solved) r.qp_unsolved++;
-    r.qp_infeasible += (a.infeasible != 0);
     r.polish_ok += a.certified;
     r.polish_attempts += a.polish_attempts;
     r.pri_res = a.pri; r.dua_res = a.dua;
+    if (qp0) {
+      if (!a.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
+      forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
+      gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
+      feasible = frow < 0;
+      r.initial_feasible = feasible;
+      if (!feasible) {
+        long long npairs = (long long)N * (N - 1) / 2;
+        int k = (int)(frow / npairs); long long p = frow - (long long)k * npairs;
+        int i = 0; while (p >= N - 1 - i) { p -= N - 1 - i; ++i; }
+        r.first_violation[0] = k; r.first_violation[1] = i; r.first_violation[2] = i + 1 + (int)p;
+        r.first_violation_dist = fdist;
+        if (k == 0 && r.status == SCP_B200_STATUS_OK) r.status = SCP_B200_STATUS_START_TOO_CLOSE;
+      }
+      qp0 = 0;
+      continue;
+    }
+    if (!a.solved) r.qp_unsolved++;
+    r.qp_infeasible += (a.infeasible != 0);
     // rel step on accelerations, scp.py:157-163
     SCP_PHASE(c) {
       double s0 = 0, s1 = 0;
@@ -1923,6 +1975,7 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
   r.scp_iterations = it; r.converged = converged;
   r.cycles_total += SCP_CLOCK() - t_begin; r.cycles_admm += c.t_admm; r.cycles_polish += c.t_polish; r.polish_rounds += c.polish_rounds;
   r.cycles_pbuild += c.t_pbuild; r.cycles_psolve += c.t_psolve; r.cycles_peval += c.t_peval; r.cycles_papply += c.t_papply;
+  r.device_ns += SCP_NANOS() - ns_begin;
   if (resumable && r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
     // suspend: the iterate goes to the scenario's acc output, the counters to its record
     r.reserved2 = 1;

@@ -79,9 +79,15 @@ struct Dev {
   double* peerP1[8];
   unsigned* peerFlag[8];       // flag arrays of every rank: flag[g] = k_iter launches rank g has completed and published
   unsigned *flag, *iter_no, *cta_done, *err;
+  long long* t0ns;             // %globaltimer at the start of the solve (k_init)
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
 __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
   atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
@@ -160,7 +166,7 @@ __global__ void k_init(const __grid_constant__ Dev d) {
       r.first_violation[0] = r.first_violation[1] = r.first_violation[2] = -1;
       r.min_separation = INFINITY;
       d.rec[b] = r;
-      if (b == 0) *d.done = 0;
+      if (b == 0) { *d.done = 0; *d.t0ns = globaltimer_ns(); }
     }
   }
 }
@@ -1249,10 +1255,16 @@ __global__ void k_control2(const __grid_constant__ Dev d) {
   State& S = d.st[b];
   if (S.phase >= 2 || !(S.flags & FL_SCAN)) return;
   const double minsep = combine(d, b, R_MINSEP, 2), first = combine(d, b, R_FIRST, 2);
-  const double bad = combine(d, b, R_BAD, 1), maxd = combine(d, b, R_MAXD, 0);
+  const double bad = combine(d, b, R_BAD, 1), maxd = combine(d, b, R_MAXD, 0), over = combine(d, b, R_OVER, 0);
   double* sl = d.slab + (size_t)b * NRED;
-  sl[R_MINSEP] = INFINITY; sl[R_FIRST] = INFINITY; sl[R_BAD] = 0.0; sl[R_MAXD] = 0.0;
+  sl[R_MINSEP] = INFINITY; sl[R_FIRST] = INFINITY; sl[R_BAD] = 0.0; sl[R_MAXD] = 0.0; sl[R_OVER] = 0.0;
   scp_b200_record& r = d.rec[b];
+  if (over > 0.0) {
+    // the verification found a violated row that does not fit the per-(step, agent) candidate capacity: the iterate is
+    // NOT the minimiser of the full QP (the reference carries every pair row, scp.py:487-552) -- reported, never silent
+    r.reserved2 |= 4;
+    if (bad == 0.0) S.qp_solved = 0;
+  }
   S.minsep = minsep;
   r.pri_res = S.pri; r.dua_res = S.dua;
   int finish = 0, next_iter = 0;
@@ -1284,8 +1296,6 @@ __global__ void k_control2(const __grid_constant__ Dev d) {
       if (copies != S.copies) S.flags |= FL_FACTOR;
       S.copies = copies; S.ncand += bad;
       if (copies > r.max_copies) r.max_copies = copies;
-      if (combine(d, b, R_OVER, 0) > 0.0) r.reserved2 |= 4;
-      sl[R_OVER] = 0.0;
       start_qp(S, d);
     } else {
       if (!S.qp_solved) { r.qp_unsolved++; if (S.stalled) r.qp_infeasible++; }
@@ -1328,7 +1338,7 @@ __global__ void k_finalize(const __grid_constant__ Dev d) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d.B) return;
   State& S = d.st[b];
-  if (S.phase < 2 && (S.flags & FL_FINISH)) { S.phase = 2; atomicAdd(d.done, 1); }
+  if (S.phase < 2 && (S.flags & FL_FINISH)) { S.phase = 2; d.rec[b].device_ns = globaltimer_ns() - *d.t0ns; atomicAdd(d.done, 1); }
   S.flags = 0;
 }
 
@@ -1562,6 +1572,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
   else d.gath = d.slab;
   if ((rc = dev_alloc(s, &d.st, (size_t)B))) return fail(rc);
   if ((rc = dev_alloc(s, &d.done, 1))) return fail(rc);
+  if ((rc = dev_alloc(s, &d.t0ns, 1))) return fail(rc);
   if ((rc = dev_alloc(s, &d.flag, 16))) return fail(rc);
   if (cudaMemset(d.flag, 0, 16 * sizeof(unsigned)) != cudaSuccess) return fail(scp_b200_set_error(100, "memset"));
   d.iter_no = d.flag + 8; d.cta_done = d.flag + 9; d.err = d.flag + 10;

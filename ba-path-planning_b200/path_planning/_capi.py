@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 MAX_SCP_ITER = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libscp_b200.so")
@@ -54,6 +54,9 @@ class Problem(C.Structure):
         ("team_mode", C.c_int32),
         ("lazy_rows", C.c_int32),
         ("momentum_pct", C.c_int32),
+        ("max_admm_iter_qp0", C.c_int32),
+        ("cap_halving", C.c_int32),
+        ("polish_max_failed", C.c_int32),
     ]
 
 
@@ -86,6 +89,7 @@ class Record(C.Structure):
         ("cycles_psolve", C.c_int64),
         ("cycles_peval", C.c_int64),
         ("cycles_papply", C.c_int64),
+        ("device_ns", C.c_int64),
         ("rel_step", C.c_double * MAX_SCP_ITER),
     ]
 
@@ -212,6 +216,7 @@ def record_to_dict(r: Record) -> dict:
         cycles_peval=int(r.cycles_peval), cycles_papply=int(r.cycles_papply),
         first_violation_dist=float(r.first_violation_dist), min_separation=float(r.min_separation),
         objective=float(r.objective), pri_res=float(r.pri_res), dua_res=float(r.dua_res), cand_row_iters=float(r.cand_row_iters),
-        reserved2=int(r.reserved2),
+        reserved2=int(r.reserved2), device_ns=int(r.device_ns),
+        candidate_overflow=bool(int(r.reserved2) & 4),   # streaming solver: collision rows dropped for lack of slots
         rel_steps=[float(r.rel_step[i]) for i in range(n)],
     )

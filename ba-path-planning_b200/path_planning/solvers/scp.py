@@ -107,6 +107,9 @@ class SCP:
         start = time.time()
         if max_iterations > _capi.MAX_SCP_ITER:
             raise ValueError(f"max_iterations > {_capi.MAX_SCP_ITER} not supported")
+        if any(a is None for a in (self.initial_positions, self.initial_velocities, self.final_positions,
+                                   self.final_velocities)):
+            raise ValueError("set_initial_states() and set_final_states() must be called before generate_trajectories()")
         p = self._problem(max_iterations)
         N, K = self.N, self.K
         buf = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
@@ -139,6 +142,8 @@ class SCP:
                 self._say(f"Converged after {it+1} iterations.")
         if r["qp_unsolved"]:
             self._say(f"Warning: {r['qp_unsolved']} subproblem(s) hit the ADMM iteration limit")
+        if r.get("candidate_overflow"):
+            print("Warning: collision rows were dropped (candidate capacity of the streaming solver exceeded)")
         self.trajectories = {"positions": pos, "velocities": vel, "accelerations": acc}
         self._say(f"Trajectory generation completed in {time.time() - start:.3f} seconds")
         return self.trajectories

@@ -7,8 +7,9 @@ at N=1000, K=100) and then runs `scp_b200_linearize_range` on its share of the p
 separation and the first violating row (the gate of scp.py:597-615) are combined with a MIN all-reduce.
 Blocks are balanced by pair count (agent i owns N-1-i rows per step), not by agent count.
 
-Status: this shards the pairwise kernel -- the O(N^2 K) part of an SCP iteration.  The sharded QP solve that
-consumes the rows (all-gather per ADMM iteration, distributed polish) is not built yet.
+This module shards the pairwise kernel alone -- the O(N^2 K) part of an SCP iteration.  The complete agent-sharded
+solve (QP included: all-gather or peer-memory exchange of the positions per ADMM iteration) is
+`solvers/stream.py::StreamSolver(..., sharded=True)` on top of `scp_b200_stream_*`.
 """
 
 from __future__ import annotations

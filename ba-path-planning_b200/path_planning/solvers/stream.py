@@ -57,11 +57,9 @@ class StreamSolver:
                 dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
                 idbuf = (C.c_char * 128).from_buffer_copy(box[0])
         self.lo, self.hi = agent_block(self.N, self.rank, self.world)
-        h = C.c_void_p()
-        _capi.check(self.lib.scp_b200_stream_create(
-            C.byref(self.problem), self.B, int(max_candidates), self.rank, self.world,
-            C.cast(idbuf, C.c_void_p) if idbuf is not None else None, C.byref(h)))
-        self._h = h
+        self.max_candidates = int(max_candidates)
+        self._h = None
+        self._create(idbuf)
         self.exchange = "none" if self.world == 1 else "nccl"
         if self.world > 1 and peer_exchange:
             # peer-memory exchange of the position slices (NVLink stores + flags) instead of an NCCL call per iteration
@@ -85,6 +83,35 @@ class StreamSolver:
             dist.barrier(group=group)
         self.last_device_ms = None
         self.last_macro_steps = None
+
+    MAX_CANDIDATES_LIMIT = 48          # MAXC_MAX in csrc/scp_stream.cu
+
+    def _create(self, idbuf=None):
+        if self._h:
+            self.lib.scp_b200_stream_destroy(self._h)
+            self._h = None
+        h = C.c_void_p()
+        _capi.check(self.lib.scp_b200_stream_create(
+            C.byref(self.problem), self.B, self.max_candidates, self.rank, self.world,
+            C.cast(idbuf, C.c_void_p) if idbuf is not None else None, C.byref(h)))
+        self._h = h
+
+    def _overflow_retry(self, records):
+        """True when a scenario dropped collision rows for lack of candidate slots and the solver was rebuilt with
+        twice the capacity (single-GPU solver only; the caller solves again).  Otherwise warns if rows were dropped."""
+        if not any(r["candidate_overflow"] for r in records):
+            return False
+        cap = min(self.MAX_CANDIDATES_LIMIT, max(self.N - 1, 1))
+        if self.world == 1 and self.max_candidates < cap:
+            self.max_candidates = min(cap, 2 * self.max_candidates)
+            self._create()
+            return True
+        import warnings
+
+        n = sum(1 for r in records if r["candidate_overflow"])
+        warnings.warn(f"streaming SCP solver: {n} scenario(s) dropped collision rows (more than {self.max_candidates} "
+                      "partners per agent and step); their subproblems are reported as unsolved", RuntimeWarning)
+        return False
 
     def close(self):
         if getattr(self, "_h", None):
@@ -110,9 +137,12 @@ class StreamSolver:
         rec = torch.empty(B * C.sizeof(_capi.Record), dtype=torch.uint8, device=self.device)
         ms, steps = C.c_float(0.0), C.c_int64(0)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _capi.check(self.lib.scp_b200_stream_solve(
-            self._h, p0.data_ptr(), v0.data_ptr(), pf.data_ptr(), vf.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
-            out[2].data_ptr(), rec.data_ptr(), st, C.byref(ms), C.byref(steps)))
+        while True:
+            _capi.check(self.lib.scp_b200_stream_solve(
+                self._h, p0.data_ptr(), v0.data_ptr(), pf.data_ptr(), vf.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                out[2].data_ptr(), rec.data_ptr(), st, C.byref(ms), C.byref(steps)))
+            if not self._overflow_retry(self.records_from_bytes(rec)):
+                break
         self.last_device_ms, self.last_macro_steps = float(ms.value), int(steps.value)
         return out[0], out[1], out[2], rec
 
@@ -130,8 +160,12 @@ class StreamSolver:
         recs = (_capi.Record * self.B)()
         ms, steps = C.c_float(0.0), C.c_int64(0)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _capi.check(self.lib.scp_b200_stream_solve_host(
-            self._h, ptr(p0), ptr(v0), ptr(pf), ptr(vf), ptr(acc), ptr(pos), ptr(vel), C.cast(recs, C.c_void_p),
-            C.byref(ms), C.byref(steps)))
+        while True:
+            _capi.check(self.lib.scp_b200_stream_solve_host(
+                self._h, ptr(p0), ptr(v0), ptr(pf), ptr(vf), ptr(acc), ptr(pos), ptr(vel), C.cast(recs, C.c_void_p),
+                C.byref(ms), C.byref(steps)))
+            out = [_capi.record_to_dict(r) for r in recs]
+            if not self._overflow_retry(out):
+                break
         self.last_device_ms, self.last_macro_steps = float(ms.value), int(steps.value)
-        return ({"positions": pos, "velocities": vel, "accelerations": acc}, [_capi.record_to_dict(r) for r in recs])
+        return ({"positions": pos, "velocities": vel, "accelerations": acc}, out)

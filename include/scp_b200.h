@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCP_B200_ABI_VERSION 2
+#define SCP_B200_ABI_VERSION 3
 #define SCP_B200_MAX_SCP_ITER 32
 
 /* Problem definition shared by every scenario of a batch.
@@ -68,6 +68,11 @@ typedef struct scp_b200_problem {
                               class joins, per scenario, when a converged iterate violates it (verify-and-enlarge, as
                               for the collision rows); 0 = all box rows carried from the start */
   int32_t momentum_pct;    /* streaming solver: heavy-ball extrapolation of the collision state in percent (0: off) */
+  /* --- ABI 3 --- */
+  int32_t max_admm_iter_qp0; /* iteration cap of the initial QP (OSQP default max_iter 4000, scp.py:360); 0: max_admm_iter */
+  int32_t cap_halving;     /* 1: every subproblem of a scenario that ran into the iteration cap halves the cap of its next
+                              ones (floor 500); 0: every subproblem gets the full cap, like scp.py:442 */
+  int32_t polish_max_failed; /* failed polish attempts per subproblem before it ends on the ADMM residual test only */
 } scp_b200_problem;
 
 /* Per-scenario result record (device or host array of B records). */
@@ -93,6 +98,8 @@ typedef struct scp_b200_record {
   int32_t polish_rounds;   /* add/drop rounds over all polish attempts */
   int32_t reserved2;
   int64_t cycles_pbuild, cycles_psolve, cycles_peval, cycles_papply; /* polish breakdown */
+  int64_t device_ns;       /* ABI 3: nanoseconds of GPU time spent on THIS scenario (one-CTA solver: sum over its quanta,
+                              %globaltimer; streaming solver: batch start to the moment the scenario finished) */
   double rel_step[SCP_B200_MAX_SCP_ITER]; /* scp.py:157-160, one per trip */
 } scp_b200_record;
 
