@@ -114,6 +114,13 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     }
     c.a_P = ptr[0]; c.a_F = ptr[1]; c.a_x = ptr[2]; c.a_vp = ptr[3]; c.a_vv = ptr[4]; c.a_vj = ptr[5]; c.a_va = ptr[6]; c.a_rhs = ptr[7];
     c.fused_epl = fused_ok ? 2 : 0;
+    // region the polish factors in (hot arrays are assigned contiguously, in this order, rhs last and never parked)
+    c.pol_smem = nullptr; c.pol_smem_doubles = 0;
+    for (int a = 0; a < 7; ++a) {
+      const bool hot = (hot_mask >> a) & 1;
+      c.hot_s[a] = hot ? ptr[a] : nullptr; c.hot_g[a] = glob[a];
+      if (hot) { if (!c.pol_smem) c.pol_smem = ptr[a]; c.pol_smem_doubles += QK; }
+    }
   }
   // Work queue of quanta (one SCP iteration each).  Items 0..B-1 are the scenarios themselves; a scenario that is not
   // finished after its quantum is pushed to the tail, so long scenarios interleave with short ones and the batch
@@ -176,6 +183,8 @@ scp_solve_team_kernel(const __grid_constant__ scp::Params g, int B, const double
   c.fused_epl = 0; c.fused_rows = nullptr;
   c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F; c.a_x = c.wd + g.L.x; c.a_vp = c.wd + g.L.vp;
   c.a_vv = c.wd + g.L.vv; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va; c.a_rhs = c.wd + g.L.rhs;
+  c.pol_smem = nullptr; c.pol_smem_doubles = 0;
+  for (int a = 0; a < 7; ++a) { c.hot_s[a] = nullptr; c.hot_g[a] = nullptr; }
   for (int b = 0; b < B; ++b) {
     const size_t s2 = (size_t)b * c.N * 2, s3 = (size_t)b * c.N * c.K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;

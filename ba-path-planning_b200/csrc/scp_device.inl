@@ -99,7 +99,7 @@ struct Layout {
   size_t Minv, N0, Qm, x, xprev, rhs, vj, va, vv, vp, posrow, velrow, P, Pbar, F, FY, off, deq, mu;
   size_t c_eta, c_bound, lam, scr, red, n_double;
   size_t xt, Pt, yj, ya, yv, yp, plam, pL, pG, prhs, py, pb_, pex, pey, pcv, pcp;   // polish (doubles)
-  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec, ppos, pcpos, pcown, pid, chg;   // polish (ints)
+  size_t pmark, pcmark, ptype, pq, pj2, pk, psgn, pdec, pcdec, ppos, pcpos, pcown, pid, chg, pslot, pdirty, pdl;   // polish (ints)
   size_t pscore, pcscore;                                               // polish (doubles)
   int pcap;
   size_t cnt, coff, c_j, flags, n_int;
@@ -138,6 +138,7 @@ Layout make_layout(int N, int K) {
   L.cnt = takei((size_t)N * K + 1); L.coff = takei((size_t)N * K + 1); L.c_j = takei(L.cap); L.flags = takei(((size_t)N * N * K + 3) / 4);
   L.pmark = takei(4 * QK); L.pcmark = takei(L.cap); L.pdec = takei(4 * QK); L.pcdec = takei(L.cap);
   L.ppos = takei(4 * QK); L.pcpos = takei(L.cap); L.pcown = takei(L.cap); L.pid = takei(L.pcap); L.chg = takei(L.pcap);
+  L.pslot = takei(L.pcap); L.pdirty = takei(L.pcap); L.pdl = takei(L.pcap);
   L.ptype = takei(L.pcap); L.pq = takei(L.pcap); L.pj2 = takei(L.pcap); L.pk = takei(L.pcap); L.psgn = takei(L.pcap);
   L.n_int = p;
   return L;
@@ -169,6 +170,14 @@ struct Ctx {
   scp_b200_record* rec;
   int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
   double* fused_rows;           // per-warp right-hand-side rows (shared)
+  // The polish factors its Gram matrix in shared memory: the hot arrays P, F, x, vp, vv, vj, va (everything but rhs)
+  // are parked in their global homes for the duration of an attempt and the a_* pointers follow them.
+  int pol_no_smem;              // a set outgrew the shared-memory region: later attempts of this scenario use the slot scratch
+  double* pol_A;                // where Ainv of the running attempt lives (parked shared region or slot scratch)
+  double* pol_smem;             // start of the parked region (null: nothing to park -- team kernel, test build)
+  size_t pol_smem_doubles;
+  double* hot_s[7];             // shared-memory copies (null when the array lives in global memory anyway)
+  double* hot_g[7];             // global homes
   int polish_rounds;            // add/drop rounds over all attempts of this scenario
   int pol_valid, pol_n, pol_use_col, pol_col_stale;   // polish list/inverse state carried between attempts
   long long t_pbuild, t_psolve, t_peval, t_papply;
@@ -1038,108 +1047,238 @@ SCP_DEV double polish_rhs_entry(Ctx& c, const PGeom& g, int r) {
   return 2.0 * (axd - (c.wd + c.g->L.pb_)[r]);
 }
 
-// Row in list slot n joins the set: returns 0 on a non-positive Schur complement.
-SCP_DEV int polish_add(Ctx& c, const PGeom& g, int n) {
-  const int ld = c.g->L.pcap;
-  double* A = c.wd + c.g->L.pL;
-  double* G0 = c.wd + c.g->L.pG;
-  double* gv = c.wd + c.g->L.scr;                // n+1
-  double* u = gv + c.g->L.pcap;                  // n
-  double* red = c.sh;
+// ---- active-set list maintenance and the dense solve (G0 + delta diag G0) y = rhs
+// Kept per list: the exact Gram matrix G0 (full symmetric storage in the slot scratch, stride pcap; rows are closed
+// forms and are recomputed in parallel for every list position that changed) and Ainv = (G0 + delta diag G0)^-1 as a
+// PACKED symmetric matrix (row-major lower triangle: A(i,j), i >= j, at i(i+1)/2 + j -- appending a row appends
+// storage).  During a polish attempt Ainv lives in SHARED memory on the GPU (the ADMM's hot arrays are parked in
+// their global homes meanwhile); between attempts it is saved to the slot scratch.  A fresh list is inverted by
+// symmetric Gauss-Jordan sweeps, later rows enter / leave with O(n^2) bordered-inverse updates / rank-one
+// downdates -- the same algebra as round 1, which ran out of L2 (43 % of the solver's cycles).
+SCP_DEV size_t sp_row(int i) { return ((size_t)i * (size_t)(i + 1)) / 2; }
+SCP_DEV size_t sp_idx(int i, int j) { return i >= j ? sp_row(i) + j : sp_row(j) + i; }
+
+// (i, j) of packed index e, branch free: float square root + two integer corrections (data-dependent loops cost
+// ~30 cycles per trip on the GPU; measured: this loop body was 5x slower with an incremental (i, j) walk)
+SCP_DEV void sp_decode(long long e, int& i, int& j) {
+  int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+  r -= ((long long)sp_row(r) > e);
+  r += ((long long)sp_row(r + 1) <= e);
+  r -= ((long long)sp_row(r) > e);
+  r += ((long long)sp_row(r + 1) <= e);
+  i = r; j = (int)(e - (long long)sp_row(r));
+}
+
+// A_ij += s v_i v_j over the packed lower triangle of an n x n matrix, skipping row/column `skip` (-1: none)
+SCP_DEV void sp_rank1(Ctx& c, double* A, int n, const double* v, double s, int skip) {
+  const long long total = (long long)sp_row(n);
   SCP_PHASE(c) {
-    const PRow nw = load_prow(c, n);
-    for (int i = tid; i <= n; i += c.nthreads) {
-      const PRow a = load_prow(c, i);
-      const double v = gram_entry(g, a, nw);
-      gv[i] = v; G0[(size_t)n * ld + i] = v; G0[(size_t)i * ld + n] = v;
+    for (long long e = tid; e < total; e += c.nthreads) {
+      int i, j;
+      sp_decode(e, i, j);
+      if (i != skip && j != skip) A[e] += s * v[i] * v[j];
     }
-    if (tid == 0) (c.wd + c.g->L.prhs)[n] = polish_rhs_entry(c, g, n);
   }
   SCP_SYNC(c);
+}
+
+// out = A x for the packed symmetric A.  GPU, one-CTA team: one warp per row, lanes stride over the columns and the
+// partial sums meet in a shuffle reduction (a dependent fp64 FMA chain costs 45 cycles per link on B200).
+SCP_DEV void sp_matvec(Ctx& c, const double* A, int n, const double* x, double* out, int accumulate) {
+#ifndef SCP_EMU
+  if (c.team == 1) {
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x >> 5; i < n; i += nw) {
+      const double* row = A + sp_row(i);
+      double a = 0.0;
+      for (int j = lane; j <= i; j += 32) a += row[j] * x[j];
+      for (int j = i + 1 + lane; j < n; j += 32) a += A[sp_row(j) + i] * x[j];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+      if (lane == 0) out[i] = (accumulate ? out[i] : 0.0) + a;
+    }
+    __syncthreads();
+    return;
+  }
+#endif
   SCP_PHASE(c) {
-    double part = 0.0;
     for (int i = tid; i < n; i += c.nthreads) {
-      double acc = 0.0;
-      for (int j = 0; j < n; ++j) acc += A[(size_t)j * ld + i] * gv[j];
-      u[i] = acc; part += acc * gv[i];
+      const double* row = A + sp_row(i);
+      double a0 = 0.0, a1 = 0.0;
+      int j = 0;
+      for (; j + 1 <= i; j += 2) { a0 += row[j] * x[j]; a1 += row[j + 1] * x[j + 1]; }
+      if (j <= i) a0 += row[j] * x[j];
+      for (j = i + 1; j < n; ++j) a1 += A[sp_row(j) + i] * x[j];
+      out[i] = (accumulate ? out[i] : 0.0) + (a0 + a1);
     }
-    red[tid] = part;
   }
   SCP_SYNC(c);
-  const double gtu = reduce_finish(c, 0, 1);
-  const double gnn = gv[n];
-  const double sch = gnn * (1.0 + 1e-11) - gtu;
-  if (!(sch > 0.0)) return 0;
-  const double is = 1.0 / sch;
+}
+
+// Ainv of the first n list rows from scratch: A <- G0 (+ relative diagonal shift), then n symmetric Gauss-Jordan
+// sweeps (sweep k: A_ij -= A_ik A_kj / A_kk, A_ik /= A_kk, A_kk = -1/A_kk) leave -inverse; negated at the end.
+// Returns 0 on a non-positive pivot (dependent active rows).
+SCP_DEV int polish_invert(Ctx& c, double* A, int n) {
+  const int ld = c.g->L.pcap;
+  const double* G0 = c.wd + c.g->L.pG;
+  double* col = c.sh + 3 * (size_t)c.rs;          // reduction column 3 is free here (n <= pcap <= 1024 <= rs)
   SCP_PHASE(c) {
-    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
-      const double uc = u[col] * is;
-      double* Ac = A + (size_t)col * ld;
-      for (int row = tid & 31; row < n; row += 32) Ac[row] += u[row] * uc;
+    for (int e = tid; e < n * n; e += c.nthreads) {
+      const int i = e / n, j = e - i * n;
+      if (j <= i) A[sp_row(i) + j] = (i == j) ? G0[(size_t)i * ld + j] * (1.0 + 1e-11) : G0[(size_t)j * ld + i];
     }
-    for (int i = tid; i < n; i += c.nthreads) { A[(size_t)n * ld + i] = -u[i] * is; A[(size_t)i * ld + n] = -u[i] * is; }
-    if (tid == 0) A[(size_t)n * ld + n] = is;
+  }
+  SCP_SYNC(c);
+  for (int k = 0; k < n; ++k) {
+    SCP_PHASE(c) { for (int i = tid; i < n; i += c.nthreads) col[i] = A[sp_idx(i, k)]; }
+    SCP_SYNC(c);
+    const double akk = col[k];
+    if (!(akk > 0.0)) return 0;                   // uniform: every thread reads the same value
+    const double d = 1.0 / akk;
+    sp_rank1(c, A, n, col, -d, k);
+    SCP_PHASE(c) {
+      for (int i = tid; i < n; i += c.nthreads) A[sp_idx(i, k)] = (i == k) ? -d : col[i] * d;
+    }
+    SCP_SYNC(c);
+  }
+  // after all sweeps the pivots are negative definite: A = -(G)^-1 with the swept sign convention folded in
+  SCP_PHASE(c) {
+    const long long total = (long long)sp_row(n);
+    for (long long e = tid; e < total; e += c.nthreads) A[e] = -A[e];
   }
   SCP_SYNC(c);
   return 1;
 }
 
-// Row at list position p leaves the set; the last row moves into the hole.  Returns the new n.
-SCP_DEV int polish_drop(Ctx& c, int p, int n) {
-  const int ld = c.g->L.pcap, K = c.K, QK = c.Q * K;
-  double* A = c.wd + c.g->L.pL;
-  double* G0 = c.wd + c.g->L.pG;
-  double* cpv = c.wd + c.g->L.scr;
-  SCP_PHASE(c) { for (int i = tid; i < n; i += c.nthreads) cpv[i] = A[(size_t)p * ld + i]; }
+// Row in list slot n joins Ainv (bordered inverse, Schur complement of the new row).  0 on a non-positive complement.
+SCP_DEV int polish_add(Ctx& c, double* A, int n) {
+  const int ld = c.g->L.pcap;
+  const double* G0 = c.wd + c.g->L.pG;
+  double* gv = c.sh + 3 * (size_t)c.rs;           // n+1 Gram entries of the new row
+  double* u = c.sh + 2 * (size_t)c.rs;            // n
+  double* red = c.sh;
+  SCP_PHASE(c) { for (int i = tid; i <= n; i += c.nthreads) gv[i] = G0[(size_t)n * ld + i]; }
   SCP_SYNC(c);
-  const double iapp = 1.0 / cpv[p];
+  sp_matvec(c, A, n, gv, u, 0);
   SCP_PHASE(c) {
-    for (int col = tid >> 5; col < n; col += c.nthreads >> 5) {
-      const double cc = cpv[col] * iapp;
-      double* Ac = A + (size_t)col * ld;
-      for (int row = tid & 31; row < n; row += 32) Ac[row] -= cpv[row] * cc;
-    }
+    double part = 0.0;
+    for (int i = tid; i < n; i += c.nthreads) part += u[i] * gv[i];
+    red[tid] = part;
   }
   SCP_SYNC(c);
-  const int last = n - 1;
-  if (p != last) {
-    SCP_PHASE(c) {
-      for (int i = tid; i < n; i += c.nthreads) { A[(size_t)p * ld + i] = A[(size_t)last * ld + i]; G0[(size_t)p * ld + i] = G0[(size_t)last * ld + i]; }
-    }
-    SCP_SYNC(c);
-    SCP_PHASE(c) {
-      for (int i = tid; i < last; i += c.nthreads) { A[(size_t)i * ld + p] = A[(size_t)i * ld + last]; G0[(size_t)i * ld + p] = G0[(size_t)i * ld + last]; }
-      if (tid == 0) {
-        int* ptype = c.wi + c.g->L.ptype; int* pq = c.wi + c.g->L.pq; int* pj2 = c.wi + c.g->L.pj2;
-        int* pk = c.wi + c.g->L.pk; int* psgn = c.wi + c.g->L.psgn; int* pid = c.wi + c.g->L.pid;
-        ptype[p] = ptype[last]; pq[p] = pq[last]; pj2[p] = pj2[last]; pk[p] = pk[last]; psgn[p] = psgn[last]; pid[p] = pid[last];
-        double* base = c.wd;
-        const size_t offs[7] = {c.g->L.pb_, c.g->L.pex, c.g->L.pey, c.g->L.pcv, c.g->L.pcp, c.g->L.prhs, c.g->L.py};
-        for (int f = 0; f < 7; ++f) (base + offs[f])[p] = (base + offs[f])[last];
-        const int id = pid[p];
-        if (id < 4 * QK) (c.wi + c.g->L.ppos)[id] = p; else (c.wi + c.g->L.pcpos)[id - 4 * QK] = p;
-      }
-    }
-    SCP_SYNC(c);
+  const double gtu = reduce_finish(c, 0, 1);
+  const double sch = gv[n] * (1.0 + 1e-11) - gtu;
+  if (!(sch > 0.0)) return 0;
+  const double is = 1.0 / sch;
+  sp_rank1(c, A, n, u, is, -1);
+  SCP_PHASE(c) {
+    double* row = A + sp_row(n);
+    for (int i = tid; i < n; i += c.nthreads) row[i] = -u[i] * is;
+    if (tid == 0) row[n] = is;
   }
-  return last;
+  SCP_SYNC(c);
+  return 1;
 }
 
-// Applies the pending mark changes (pdec vs pmark / pcdec vs pcmark, score >= threshold) one row at a time.
-// Returns the new n, or -1 when the set outgrows the list or an update breaks down.
-SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_add, double thr_drop) {
+// Row at list position p leaves Ainv (rank-one downdate); the last row (n-1) moves into the hole.
+SCP_DEV void polish_drop(Ctx& c, double* A, int p, int n) {
+  double* cpv = c.sh + 3 * (size_t)c.rs;
+  double* lastrow = c.sh + 2 * (size_t)c.rs;
+  SCP_PHASE(c) { for (int i = tid; i < n; i += c.nthreads) cpv[i] = A[sp_idx(p, i)]; }
+  SCP_SYNC(c);
+  sp_rank1(c, A, n, cpv, -1.0 / cpv[p], p);
+  const int last = n - 1;
+  if (p != last) {
+    SCP_PHASE(c) { for (int i = tid; i < n; i += c.nthreads) lastrow[i] = A[sp_row(last) + i]; }
+    SCP_SYNC(c);
+    SCP_PHASE(c) {
+      for (int i = tid; i < last; i += c.nthreads) if (i != p) A[sp_idx(p, i)] = lastrow[i];
+      if (tid == 0) A[sp_row(p) + p] = lastrow[last];
+    }
+    SCP_SYNC(c);
+  }
+}
+
+// y = Ainv rhs, refined against the exact G0 until the residual is at rounding level.  The incrementally updated
+// inverse drifts (and is ruined by a nearly dependent row), so the residual is the health check of the list:
+// returns 0 when it cannot be brought down, and the caller rebuilds the list from scratch on its next attempt.
+SCP_DEV int polish_solve(Ctx& c, const double* A, int n) {
+  const int ld = c.g->L.pcap;
+  const double* G0 = c.wd + c.g->L.pG;
+  const double* rhs = c.wd + c.g->L.prhs;
+  double* y = c.wd + c.g->L.py;
+  double* z = c.sh + 3 * (size_t)c.rs;
+  double* ys = c.sh + 2 * (size_t)c.rs;           // y while it is being refined (shared memory on the GPU)
+  double* red = c.sh;
+  double bnorm = 0.0;
+  int ok = -1;
+  for (int sweep = 0; sweep < 6 && ok < 0; ++sweep) {
+#ifndef SCP_EMU
+    if (c.team == 1 && sweep > 0) {
+      // z = rhs - G0 ys, one warp per row (G0 is symmetric: row r is read along its contiguous column)
+      const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      for (int r = threadIdx.x >> 5; r < n; r += nw) {
+        const double* g0 = G0 + (size_t)r * ld;
+        double a = 0.0;
+        for (int q2 = lane; q2 < n; q2 += 32) a += g0[q2] * ys[q2];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) z[r] = -a;
+      }
+      __syncthreads();
+    }
+#endif
+    SCP_PHASE(c) {
+      double zm = 0.0, bm = 0.0;
+      for (int r = tid; r < n; r += c.nthreads) {
+        double acc = rhs[r];
+#ifndef SCP_EMU
+        if (c.team == 1) { if (sweep > 0) acc += z[r]; }
+        else
+#endif
+        if (sweep > 0) for (int q2 = 0; q2 < n; ++q2) acc -= G0[(size_t)q2 * ld + r] * ys[q2];
+        z[r] = acc;
+        zm = SCP_FMAX(zm, fabs(acc)); bm = SCP_FMAX(bm, fabs(rhs[r]));
+      }
+      red[tid] = zm; red[c.rs + tid] = bm;
+    }
+    SCP_SYNC(c);
+    const double znorm = reduce_finish(c, 0, 0);
+    if (sweep == 0) bnorm = reduce_finish(c, 1, 0);
+    if (!(znorm == znorm)) ok = 0;
+    else if (sweep > 0 && znorm <= 1e-11 * (1.0 + bnorm)) ok = 1;
+    else if (sweep == 5) ok = znorm <= 1e-9 * (1.0 + bnorm);
+    else sp_matvec(c, A, n, z, ys, sweep > 0);
+  }
+  if (ok == 1) {
+    SCP_PHASE(c) { for (int r = tid; r < n; r += c.nthreads) y[r] = ys[r]; }
+    SCP_SYNC(c);
+  }
+  return ok == 1;
+}
+
+// Applies the pending mark changes (pdec vs pmark / pcdec vs pcmark, score >= threshold): rows leave the list (the
+// last row moves into the hole) and join it (appended); the Gram rows/columns and right-hand-side entries of every
+// list position that changed are recomputed in parallel; then Ainv follows, one row at a time (or, for a fresh list,
+// by one inversion).  Returns the new n, or -1 when the set outgrows its storage or an update breaks down.
+SCP_DEV int polish_apply(Ctx& c, const PGeom& g, double* A, int ncap, int n, int use_col, double thr_add, double thr_drop) {
   const int K = c.K, N = c.N, QK = c.Q * K;
   int* pmark = c.wi + c.g->L.pmark; int* pcmark = c.wi + c.g->L.pcmark;
   const int* pdec = c.wi + c.g->L.pdec; const int* pcdec = c.wi + c.g->L.pcdec;
   const double* pscore = c.wd + c.g->L.pscore; const double* pcscore = c.wd + c.g->L.pcscore;
   int* ppos = c.wi + c.g->L.ppos; int* pcpos = c.wi + c.g->L.pcpos; int* pid = c.wi + c.g->L.pid;
   int* chg = c.wi + c.g->L.chg;
+  int* pslot = c.wi + c.g->L.pslot;               // list slot a change fills (-1: the change only removes a row)
+  int* pdirty = c.wi + c.g->L.pdirty;             // list positions whose Gram row must be recomputed
+  int* pdl = c.wi + c.g->L.pdl;                   // [0, nd): dirty positions; [pcap/2, ...): positions dropped, in order
   const int* pcown = c.wi + c.g->L.pcown;
   const int* coff = c.wi + c.g->L.coff; const int* cj = c.wi + c.g->L.c_j;
   const int total = 4 * QK + (use_col ? c.ncand : 0);
   const int np = c.np;
   const int per = (total + np - 1) / np;
   int* part = (int*)(c.sh + 2 * (size_t)c.rs);
+  int* misc = (int*)(c.sh + 4 * (size_t)c.rs + 8);     // [1] new n, [2] dirty count, [3] drops
+  int* drops = pdl + c.g->L.pcap / 2;
   SCP_PHASE(c) {
     int cnt = 0;
     if (tid < np) for (int u = tid * per; u < total && u < (tid + 1) * per; ++u) {
@@ -1147,11 +1286,12 @@ SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_
       else { const int sidx = u - 4 * QK, nm = pcdec[sidx]; cnt += (pcown[sidx] >= 0 && nm != pcmark[sidx] && pcscore[sidx] >= (nm != 0 ? thr_add : thr_drop)); }
     }
     if (tid < np) part[tid] = cnt;
+    for (int e = tid; e < c.g->L.pcap; e += c.nthreads) pdirty[e] = 0;
   }
   SCP_SYNC(c);
   int nchg = 0;
   for (int e = 0; e < np; ++e) nchg += part[e];
-  const int chg_cap = c.g->L.pcap;
+  const int chg_cap = c.g->L.pcap / 2;
   SCP_PHASE(c) {
     int base = 0;
     if (tid < np) for (int e = 0; e < tid; ++e) base += part[e];
@@ -1164,95 +1304,114 @@ SCP_DEV int polish_apply(Ctx& c, const PGeom& g, int n, int use_col, double thr_
   }
   SCP_SYNC(c);
   if (nchg > chg_cap) nchg = chg_cap;
-  for (int ci = 0; ci < nchg; ++ci) {
-    // one row at a time: [drop the row's old entry] then [add its new one]; a single call site each for the two
-    // O(n^2) updates keeps one copy of them in the kernel
-    const int id = chg[ci];
-    const int is_col = id >= 4 * QK;
-    const int sidx = is_col ? id - 4 * QK : 0;
-    int m, nm, do_add, drop_pos = -1, ck = 0, ci_ = 0, cjj = 0;
-    if (!is_col) {
-      m = pmark[id]; nm = pdec[id];
-      if (m != 0) drop_pos = ppos[id];
-      do_add = nm != 0;
-    } else {
-      m = pcmark[sidx]; nm = pcdec[sidx];
-      const int t = pcown[sidx];
-      ck = t / N; ci_ = t - ck * N; cjj = cj[sidx];
-      if (m != 0) drop_pos = pcpos[sidx];
-      do_add = (m == 0);
-    }
-    if (drop_pos >= 0) {
-      n = polish_drop(c, drop_pos, n);
-      SCP_PHASE(c) { if (tid == 0) { if (is_col) pcpos[sidx] = -1; else ppos[id] = -1; } }
-      SCP_SYNC(c);
-    }
-    if (do_add) {
-      if (n >= c.g->L.pcap) return -1;
-      SCP_PHASE(c) {
-        if (tid == 0) {
-          if (is_col) { polish_fill_col(c, n, sidx, ck, ci_); pcpos[sidx] = n; }
-          else { polish_fill_dyn(c, n, id / QK, id % QK, nm); ppos[id] = n; }
-          pid[n] = id;
+  if (nchg == 0) return n;
+  // (1) one thread: removals (list metadata only, the positions are replayed on Ainv below) and the slots of the
+  //     rows that join
+  SCP_PHASE(c) {
+    if (tid == 0) {
+      int* ptype = c.wi + c.g->L.ptype; int* pq = c.wi + c.g->L.pq; int* pj2 = c.wi + c.g->L.pj2;
+      int* pk = c.wi + c.g->L.pk; int* psgn = c.wi + c.g->L.psgn;
+      const size_t offs[6] = {c.g->L.pb_, c.g->L.pex, c.g->L.pey, c.g->L.pcv, c.g->L.pcp, c.g->L.prhs};
+      int nn = n, ndrop = 0;
+      for (int ci = 0; ci < nchg; ++ci) {
+        const int id = chg[ci];
+        const int is_col = id >= 4 * QK, sidx = is_col ? id - 4 * QK : 0;
+        const int m = is_col ? pcmark[sidx] : pmark[id];
+        if (m == 0) continue;
+        const int p = is_col ? pcpos[sidx] : ppos[id], last = nn - 1;
+        if (is_col) pcpos[sidx] = -1; else ppos[id] = -1;
+        if (p != last) {
+          ptype[p] = ptype[last]; pq[p] = pq[last]; pj2[p] = pj2[last]; pk[p] = pk[last]; psgn[p] = psgn[last]; pid[p] = pid[last];
+          for (int f = 0; f < 6; ++f) (c.wd + offs[f])[p] = (c.wd + offs[f])[last];
+          const int mid = pid[p];
+          if (mid < 4 * QK) ppos[mid] = p; else pcpos[mid - 4 * QK] = p;
+          pdirty[p] = 1;
         }
+        drops[ndrop++] = p;
+        nn = last;
       }
-      SCP_SYNC(c);
-      if (!polish_add(c, g, n)) return -1;
-      ++n;
+      int fail = 0;
+      for (int ci = 0; ci < nchg; ++ci) {
+        const int id = chg[ci];
+        const int is_col = id >= 4 * QK, sidx = is_col ? id - 4 * QK : 0;
+        const int joins = is_col ? (pcmark[sidx] == 0) : (pdec[id] != 0);
+        if (joins && nn < ncap) { pslot[ci] = nn; pdirty[nn] = 1; ++nn; }
+        else { pslot[ci] = -1; if (joins) fail = 1; }
+      }
+      misc[1] = fail ? -1 : nn; misc[3] = ndrop;
     }
+  }
+  SCP_SYNC(c);
+  const int n_new = misc[1], ndrop = misc[3];
+  if (n_new < 0) return -1;
+  // (2) one thread per change: fill the slot of a joining row, update the marks
+  SCP_PHASE(c) {
+    for (int ci = tid; ci < nchg; ci += c.nthreads) {
+      const int id = chg[ci], slot = pslot[ci];
+      if (id < 4 * QK) {
+        const int nm = pdec[id];
+        if (slot >= 0) { polish_fill_dyn(c, slot, id / QK, id % QK, nm); pid[slot] = id; ppos[id] = slot; }
+        pmark[id] = nm;
+      } else {
+        const int sidx = id - 4 * QK, nm = pcdec[sidx];
+        const int t = pcown[sidx], ck = t / N, ci_ = t - ck * N, cjj = cj[sidx];
+        if (slot >= 0) { polish_fill_col(c, slot, sidx, ck, ci_); pid[slot] = id; pcpos[sidx] = slot; }
+        pcmark[sidx] = nm;
+        for (int s2 = coff[ck * N + cjj]; s2 < coff[ck * N + cjj + 1]; ++s2) if (cj[s2] == ci_) pcmark[s2] = nm;   // mirror entry
+      }
+    }
+    if (tid == 0) {
+      int nd = 0;
+      for (int p = 0; p < n_new; ++p) if (pdirty[p]) pdl[nd++] = p;
+      misc[2] = nd;
+    }
+  }
+  SCP_SYNC(c);
+  // (3) Gram rows / columns and right-hand sides of the changed positions (final list)
+  const int nd = misc[2];
+  {
+    const int ld = c.g->L.pcap;
+    double* G0 = c.wd + c.g->L.pG;
+    double* prhs = c.wd + c.g->L.prhs;
     SCP_PHASE(c) {
-      if (tid == 0) {
-        if (!is_col) pmark[id] = nm;
-        else {
-          pcmark[sidx] = nm;
-          for (int s2 = coff[ck * N + cjj]; s2 < coff[ck * N + cjj + 1]; ++s2) if (cj[s2] == ci_) pcmark[s2] = nm;   // mirror entry
-        }
+      for (int e = tid; e < nd * n_new; e += c.nthreads) {
+        const int di = e / n_new, i = e - di * n_new, p = pdl[di];
+        const PRow a = load_prow(c, p), b = load_prow(c, i);
+        const double v = gram_entry(g, a, b);
+        G0[(size_t)p * ld + i] = v; G0[(size_t)i * ld + p] = v;
+        if (i == 0) prhs[p] = polish_rhs_entry(c, g, p);
       }
     }
     SCP_SYNC(c);
   }
-  return n;
+  // (4) Ainv: replay the removals, then the rows that joined (slots n0 .. n_new-1 in order)
+  int nn = n;
+  for (int di = 0; di < ndrop; ++di) { polish_drop(c, A, drops[di], nn); --nn; }
+  if (nn == 0 && n_new > 8) return polish_invert(c, A, n_new) ? n_new : -1;
+  for (; nn < n_new; ++nn)
+    if (!polish_add(c, A, nn)) return -1;
+  return n_new;
 }
 
-// y = Ainv rhs, refined against the exact G0 until the residual is at rounding level.  The incrementally updated
-// inverse drifts (and is ruined by a nearly dependent row), so the residual is the health check of the list:
-// returns 0 when it cannot be brought down, and the caller rebuilds the list from scratch on its next attempt.
-SCP_DEV int polish_solve(Ctx& c, int n) {
-  const int ld = c.g->L.pcap;
-  const double* A = c.wd + c.g->L.pL;
-  const double* G0 = c.wd + c.g->L.pG;
-  const double* rhs = c.wd + c.g->L.prhs;
-  double* y = c.wd + c.g->L.py;
-  double* z = c.wd + c.g->L.scr;
-  double* red = c.sh;
-  double bnorm = 0.0;
-  for (int sweep = 0; sweep < 6; ++sweep) {
-    SCP_PHASE(c) {
-      double zm = 0.0, bm = 0.0;
-      for (int r = tid; r < n; r += c.nthreads) {
-        double acc = rhs[r];
-        if (sweep > 0) for (int q2 = 0; q2 < n; ++q2) acc -= G0[(size_t)q2 * ld + r] * y[q2];
-        z[r] = acc;
-        zm = SCP_FMAX(zm, fabs(acc)); bm = SCP_FMAX(bm, fabs(rhs[r]));
-      }
-      red[tid] = zm; red[c.rs + tid] = bm;
+SCP_DEV void polish_set_hot(Ctx& c, int parked) {
+  double* p[7];
+  for (int a = 0; a < 7; ++a) p[a] = (!parked && c.hot_s[a]) ? c.hot_s[a] : c.hot_g[a];
+  c.a_P = p[0]; c.a_F = p[1]; c.a_x = p[2]; c.a_vp = p[3]; c.a_vv = p[4]; c.a_vj = p[5]; c.a_va = p[6];
+}
+// hot arrays -> global homes (park) / back (unpark); no-ops when nothing is parked
+SCP_DEV void polish_park(Ctx& c, int unpark) {
+  if (!c.pol_smem) return;
+  const int QK = c.Q * c.K;
+  SCP_PHASE(c) {
+    for (int a = 0; a < 7; ++a) {
+      if (!c.hot_s[a]) continue;
+      double* src = unpark ? c.hot_g[a] : c.hot_s[a];
+      double* dst = unpark ? c.hot_s[a] : c.hot_g[a];
+      for (int e = tid; e < QK; e += c.nthreads) dst[e] = src[e];
     }
-    SCP_SYNC(c);
-    const double znorm = reduce_finish(c, 0, 0);
-    if (sweep == 0) bnorm = reduce_finish(c, 1, 0);
-    if (!(znorm == znorm)) return 0;
-    if (sweep > 0 && znorm <= 1e-11 * (1.0 + bnorm)) return 1;
-    if (sweep == 5) return znorm <= 1e-9 * (1.0 + bnorm);
-    SCP_PHASE(c) {
-      for (int r = tid; r < n; r += c.nthreads) {
-        double acc = 0.0;
-        for (int q2 = 0; q2 < n; ++q2) acc += A[(size_t)q2 * ld + r] * z[q2];
-        y[r] = (sweep > 0 ? y[r] : 0.0) + acc;
-      }
-    }
-    SCP_SYNC(c);
   }
-  return 1;
+  SCP_SYNC(c);
+  polish_set_hot(c, !unpark);
 }
 
 // One full polish.  Returns 1 when the active set is stable (KKT certificate on the carried
@@ -1328,19 +1487,47 @@ SCP_DEV int polish(Ctx& c, int with_collisions, int max_rounds) {
   SCP_SYNC(c);
   int n = fresh ? 0 : c.pol_n;
   double ta = 0.0, td = 0.0;               // score thresholds of the pending decisions (0: apply all of them)
+  // where Ainv lives during this attempt: the parked shared-memory region when the set is expected to fit (count of
+  // marked rows + 12; a set that outgrows the region fails the attempt and later attempts use the scratch), else the slot scratch; a kept list comes back from the slot scratch
+  double* Asave = c.wd + c.g->L.pL;
+  double* A = Asave;
+  int ncap = c.g->L.pcap;
+  if (c.pol_smem) {
+    SCP_PHASE(c) {
+      double cnt = 0.0;
+      for (int e = tid; e < 4 * QK; e += c.nthreads) cnt += (pdec[e] != 0);
+      if (use_col) for (int sidx = tid; sidx < c.ncand; sidx += c.nthreads) cnt += (pcown[sidx] >= 0 && pcdec[sidx] != 0);
+      red[tid] = cnt;
+    }
+    SCP_SYNC(c);
+    const int guess = (int)reduce_finish(c, 0, 1);
+    int cap_n = (int)((sqrt(8.0 * (double)c.pol_smem_doubles + 1.0) - 1.0) * 0.5);
+    while (sp_row(cap_n) + cap_n + 1 > c.pol_smem_doubles) --cap_n;
+    if (cap_n > c.g->L.pcap) cap_n = c.g->L.pcap;
+    const int want = (guess > n ? guess : n);
+    if (!c.pol_no_smem && want + 12 <= cap_n) {
+      A = c.pol_smem; ncap = cap_n;
+      if (!fresh && n > 0) {
+        const long long total = (long long)sp_row(n);
+        SCP_PHASE(c) { for (long long e = tid; e < total; e += c.nthreads) A[e] = Asave[e]; }
+        SCP_SYNC(c);
+      }
+    }
+  }
+  c.pol_A = A;
   for (int round = 0;; ++round) {
     // pending mark changes -> list / inverse: the initial guess before round 0, the decisions of round-1 afterwards
     // (ONE call site: polish_apply and the O(n^2) updates it calls exist once in the kernel)
     if (round > 0) tq = SCP_CLOCK();
-    n = polish_apply(c, g, n, use_col, ta, td);
+    n = polish_apply(c, g, A, ncap, n, use_col, ta, td);
     if (round == 0) { c.t_pbuild += SCP_CLOCK() - tq; c.pol_use_col = use_col; c.pol_col_stale = 0; }
     else c.t_papply += SCP_CLOCK() - tq;
     c.pol_n = n; c.pol_valid = n >= 0;
-    if (n < 0) return 0;
+    if (n < 0) { if (A != Asave) c.pol_no_smem = 1; return 0; }
     if (round >= max_rounds) break;
     c.polish_rounds++;
     tq = SCP_CLOCK();
-    if (n > 0 && !polish_solve(c, n)) { c.pol_valid = 0; return 0; }
+    if (n > 0 && !polish_solve(c, A, n)) { c.pol_valid = 0; return 0; }
     c.t_psolve += SCP_CLOCK() - tq;
     tq = SCP_CLOCK();
     // scatter multipliers to the dense arrays
@@ -1781,7 +1968,16 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
     }
     if (want_polish) {
       const long long t0 = SCP_CLOCK();
+      polish_park(c, 0);
       const int pol = polish(c, with_collisions, want_polish);
+      if (c.pol_valid && c.pol_A != c.wd + c.g->L.pL) {      // keep Ainv for the next attempt on this candidate set
+        const long long total = (long long)sp_row(c.pol_n);
+        double* dst = c.wd + c.g->L.pL;
+        const double* src = c.pol_A;
+        SCP_PHASE(c) { for (long long e = tid; e < total; e += c.nthreads) dst[e] = src[e]; }
+        SCP_SYNC(c);
+      }
+      polish_park(c, 1);
       c.t_polish += SCP_CLOCK() - t0;
       o.polish_attempts++;
       if (pol) { o.solved = 1; o.certified = 1; o.pri = o.dua = 0.0; break; }
@@ -1879,7 +2075,7 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
   }
 
   setup_scenario(c);
-  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0; c.pol_col_stale = 0;
+  c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0; c.pol_col_stale = 0; c.pol_no_smem = 0; c.pol_A = nullptr;
   c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
   const long long t_begin = SCP_CLOCK(), ns_begin = SCP_NANOS();
   double minsep; long long frow; double fdist;

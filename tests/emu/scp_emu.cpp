@@ -35,6 +35,8 @@ extern "C" int scp_emu_solve_batch(const scp_b200_problem* prob, int B, const do
     c.wd = wd.data(); c.wi = wi.data(); c.sm = sm.data(); c.nmat = nullptr; c.nmat_in_smem = 1; c.fused_epl = 0; c.fused_rows = nullptr;
     c.a_x = c.wd + g.L.x; c.a_rhs = c.wd + g.L.rhs; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va;
     c.a_vv = c.wd + g.L.vv; c.a_vp = c.wd + g.L.vp; c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F;
+    c.pol_smem = nullptr; c.pol_smem_doubles = 0;
+    for (int a = 0; a < 7; ++a) { c.hot_s[a] = nullptr; c.hot_g[a] = nullptr; }
     size_t s2 = (size_t)b * N * 2, s3 = (size_t)b * N * K * 2;
     c.p0 = p0 + s2; c.v0 = v0 + s2; c.pf = pf + s2; c.vf = vf + s2;
     c.acc = acc + s3; c.pos = pos + s3; c.vel = vel + s3; c.rec = rec + b;
