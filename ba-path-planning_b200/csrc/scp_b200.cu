@@ -39,7 +39,8 @@ int fail(int code, const std::string& msg) {
 
 constexpr int SOLVE_THREADS = 512;
 constexpr size_t SMEM_BASE = (4 * scp::RED + scp::SH_EXTRA) * sizeof(double);   // scp::sh_doubles(RED)
-constexpr int QUEUE_CAP = 1 << 20;                        // quanta that can be re-queued per launch
+constexpr int QUEUE_CAP = 1 << 20;                        // queue slots per launch: QLEVELS queues of QUEUE_CAP / QLEVELS
+constexpr int QLEVELS = 4;
 constexpr size_t HEADER_BYTES = 256 + (size_t)QUEUE_CAP * sizeof(int);
 constexpr size_t TEAM_SCRATCH_BYTES = (size_t)24 << 20;   // team-wide reduction columns for the cooperative kernel
 constexpr size_t SMEM_NMAT_LIMIT = 96 * 1024;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __restrict__ p0,
                  const double* __restrict__ v0, const double* __restrict__ pf, const double* __restrict__ vf,
                  double* ws_d, int* ws_i, double* acc, double* pos, double* vel, scp_b200_record* rec,
-                 unsigned int* counter, int* queue, int resumable, int nmat_in_smem, int hot_mask) {
+                 unsigned int* counter, int* queue, int qstride, int resumable, int nmat_in_smem, int hot_mask) {
   extern __shared__ double smem[];
   __shared__ int s_b, s_fresh;
   scp::Ctx c;
@@ -122,27 +123,42 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
       if (hot) { if (!c.pol_smem) c.pol_smem = ptr[a]; c.pol_smem_doubles += QK; }
     }
   }
-  // Work queue of quanta (one SCP iteration each).  Items 0..B-1 are the scenarios themselves; a scenario that is not
-  // finished after its quantum is pushed to the tail, so long scenarios interleave with short ones and the batch
-  // ends within one quantum of the balanced finish time instead of one whole scenario.
-  // header: counter[0] = head, counter[1] = pushes, counter[2] = finished scenarios; queue[] starts at -1.
+  // Work queue of quanta (one SCP iteration each).  Fresh scenarios (tickets 0..B-1) come first, so that every scenario
+  // has shown its first quantum early; a scenario that is not finished after a quantum is pushed to one of QLEVELS
+  // FIFO queues chosen by the service it has attained so far relative to the mean first quantum (< 1x, 1-2x, 2-4x,
+  // > 4x), and workers pop from the highest non-empty level: the scenarios that have already cost the most -- with the
+  // heavy-tailed solve times of this workload the ones with the most left to do -- run without waiting, instead of
+  // taking round-robin turns and finishing long after the rest (round 1: step 1096 ms against a balanced 905 ms on one
+  // GPU, 1545 ms on a rank whose longest scenario started late).
+  // header (32-bit words): [0] fresh tickets, [2] finished scenarios, [8+l] pops of level l, [16+l] pushes of level l;
+  //         64-bit words at byte 128: sum of first-quantum cycles, count.
+  unsigned long long* stat64 = (unsigned long long*)(counter + 32);
   for (;;) {
     if (threadIdx.x == 0) {
-      int b = -1;
-      const unsigned h = atomicAdd(&counter[0], 1u);
-      s_fresh = h < (unsigned)B;
-      if (h < (unsigned)B) b = (int)h;
-      else if (resumable && h - (unsigned)B < (unsigned)QUEUE_CAP) {
-        volatile int* slot = queue + (h - (unsigned)B);
-        volatile unsigned* fin = counter + 2;
+      int b = -1, fresh = 0;
+      if (*(volatile unsigned*)&counter[0] < (unsigned)B) {
+        const unsigned h = atomicAdd(&counter[0], 1u);
+        if (h < (unsigned)B) { b = (int)h; fresh = 1; }
+      }
+      if (b < 0 && resumable) {
         for (;;) {
-          const int v = *slot;
-          if (v >= 0) { b = v; break; }
-          if (*fin >= (unsigned)B) break;
-          __nanosleep(500);
+          for (int l = QLEVELS - 1; l >= 0 && b < 0; --l) {
+            const unsigned hd = *(volatile unsigned*)&counter[8 + l], tl = *(volatile unsigned*)&counter[16 + l];
+            if (hd < tl && atomicCAS(&counter[8 + l], hd, hd + 1u) == hd) {
+              volatile int* slot = queue + (size_t)l * qstride + hd;
+              int v;
+              while ((v = *slot) < 0) __nanosleep(100);       // the pusher has reserved the slot and is writing it
+              b = v;
+            }
+          }
+          if (b >= 0) break;
+          // nothing queued: this CTA retires.  A scenario still in flight is held by a CTA that pops again after
+          // pushing it, so queued work is never orphaned; the SM goes to the next launch (consecutive batches on
+          // different streams overlap: the tail of one batch runs under the head of the next)
+          break;
         }
       }
-      s_b = b;
+      s_b = b; s_fresh = fresh;
     }
     __syncthreads();
     const int b = s_b, fresh = s_fresh;
@@ -156,8 +172,16 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+      const unsigned long long att = (unsigned long long)c.rec->cycles_total;
+      if (fresh) { atomicAdd(&stat64[0], att); atomicAdd(&stat64[1], 1ull); }
       if (done) atomicAdd(&counter[2], 1u);
-      else { const unsigned t = atomicAdd(&counter[1], 1u); if (t < (unsigned)QUEUE_CAP) atomicExch(queue + t, b); }
+      else {
+        const unsigned long long n1 = *(volatile unsigned long long*)&stat64[1], s1 = *(volatile unsigned long long*)&stat64[0];
+        const double mean1 = n1 ? (double)s1 / (double)n1 : 1.0, ratio = (double)att / mean1;
+        const int l = ratio < 1.0 ? 0 : (ratio < 2.0 ? 1 : (ratio < 4.0 ? 2 : 3));
+        const unsigned t = atomicAdd(&counter[16 + l], 1u);
+        if (t < (unsigned)qstride) { __threadfence(); atomicExch(queue + (size_t)l * qstride + t, b); }
+      }
     }
   }
 }
@@ -343,8 +367,54 @@ __global__ void scp_linearize_finish_kernel(const unsigned long long* minsep_bit
   }
 }
 
+// ---------------------------------------------------------------------------------- fp64 peak probe
+// 8 independent FMA chains per thread, 512 threads per CTA, 4 CTAs per SM worth of blocks: the roofline denominator of
+// the solver kernel (its arithmetic is fp64 FMA / ADD / MNMX on the same pipe).
+__global__ void __launch_bounds__(512) scp_fp64_probe_kernel(double* out, int iters) {
+  double a[8];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) a[ch] = 1.0 + 1e-9 * (double)(threadIdx.x + ch);
+  const double m = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) a[ch] = fma(a[ch], m, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) s += a[ch];
+  if (s == 12345.678) out[0] = s;      // never true: keeps the chains alive
+}
+
 // ---------------------------------------------------------------------------------- C ABI
 extern "C" {
+
+int scp_b200_measure_fp64_peak(double* tflops_out) {
+  if (!tflops_out) return fail(1, "null argument");
+  int dev = 0, sms = 148;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  const int iters = 20000, blocks = sms * 4;
+  scp_fp64_probe_kernel<<<blocks, 512>>>(d, 200);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_OK(cudaEventRecord(e0));
+    scp_fp64_probe_kernel<<<blocks, 512>>>(d, iters);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * (double)iters * 512.0 * (double)blocks / ((double)ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CUDA_OK(cudaGetLastError());
+  *tflops_out = best;
+  return 0;
+}
 
 int scp_b200_abi_version(void) { return SCP_B200_ABI_VERSION; }
 size_t scp_b200_sizeof_problem(void) { return sizeof(scp_b200_problem); }
@@ -414,8 +484,9 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   CUDA_OK(cudaMemsetAsync(counter, 0, 256, st));
   // warm_duals keeps the multipliers of the previous subproblem in the slot scratch: a re-queued scenario may resume in
   // another slot, so that option runs every scenario start to finish in one slot
-  const int resumable = (!prob->warm_duals && (long long)B * (prob->max_scp_iter + 2) <= (long long)QUEUE_CAP) ? 1 : 0;
-  if (resumable) CUDA_OK(cudaMemsetAsync(queue, 0xFF, (size_t)B * (prob->max_scp_iter + 2) * sizeof(int), st));
+  const int qstride = B * (prob->max_scp_iter + 2);        // a scenario is pushed at most once per SCP iteration
+  const int resumable = (!prob->warm_duals && (long long)qstride * QLEVELS <= (long long)QUEUE_CAP) ? 1 : 0;
+  if (resumable) CUDA_OK(cudaMemsetAsync(queue, 0xFF, (size_t)qstride * QLEVELS * sizeof(int), st));
   int hot_mask = 0;
   const size_t nm = nmat_smem_bytes(K);
   const size_t smem = plan_smem(prob->n_agents, K, &hot_mask);
@@ -435,7 +506,7 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   } else {
     const int grid = B < slots ? B : slots;
     scp_solve_kernel<<<grid, SOLVE_THREADS, smem, st>>>(g, B, d_p0, d_v0, d_pf, d_vf, ws_d, ws_i, d_acc, d_pos,
-                                                          d_vel, d_records, counter, queue, resumable, nm ? 1 : 0, hot_mask);
+                                                          d_vel, d_records, counter, queue, qstride, resumable, nm ? 1 : 0, hot_mask);
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -443,13 +514,21 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
 
 namespace {
 constexpr int MAX_DEVICES = 64;
-struct HostCache {      // device buffers reused across scp_b200_solve_batch_host calls, one set per device
-  std::mutex mu;        // held for the whole call: calls on ONE device serialise, calls on different devices do not
-  bool init = false;
-  void* tables = nullptr; size_t tables_bytes = 0; scp_b200_problem tables_for{};
+constexpr int HOST_LANES = 2;
+// Device buffers reused across scp_b200_solve_batch_host calls, per device.  Two LANES (stream + workspace + staging
+// buffers each): two host threads calling at the same time run on different streams, so the tail of one batch (a few
+// long scenarios, most SMs already retired) overlaps the head of the next; a single caller always gets lane 0.
+struct HostLane {
+  std::mutex mu;
   void* ws = nullptr; size_t ws_bytes = 0;
   void* io = nullptr; size_t io_bytes = 0;
   cudaStream_t stream = nullptr;
+};
+struct HostCache {
+  std::mutex mu;        // guards the tables (shared by the lanes)
+  void* tables = nullptr; size_t tables_bytes = 0; scp_b200_problem tables_for{}; bool tables_valid = false;
+  std::vector<void*> retired;   // replaced tables another lane may still be reading
+  HostLane lane[HOST_LANES];
 };
 HostCache g_cache[MAX_DEVICES];
 }  // namespace
@@ -461,37 +540,49 @@ int scp_b200_solve_batch_host(const scp_b200_problem* prob, int B, const double*
   if (B <= 0) return 0;
   if (device < 0 || device >= MAX_DEVICES) return fail(1, "device index out of range");
   HostCache& hc = g_cache[device];
-  std::lock_guard<std::mutex> lock(hc.mu);
   CUDA_OK(cudaSetDevice(device));
-  if (!hc.init) {
-    CUDA_OK(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
-    hc.init = true;
-  }
+  // a free lane, else wait for lane 0
+  int li = -1;
+  for (int l = 0; l < HOST_LANES && li < 0; ++l) if (hc.lane[l].mu.try_lock()) li = l;
+  if (li < 0) { hc.lane[0].mu.lock(); li = 0; }
+  HostLane& ln = hc.lane[li];
+  std::lock_guard<std::mutex> lane_lock(ln.mu, std::adopt_lock);
+  if (!ln.stream) CUDA_OK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
   const int N = prob->n_agents, K = prob->n_steps;
-  const size_t tb = scp_b200_tables_bytes(prob);
-  if (tb > hc.tables_bytes) { if (hc.tables) cudaFree(hc.tables); CUDA_OK(cudaMalloc(&hc.tables, tb)); hc.tables_bytes = tb; memset(&hc.tables_for, 0, sizeof(hc.tables_for)); }
-  if (memcmp(&hc.tables_for, prob, sizeof(*prob)) != 0) {
-    if (int rc = scp_b200_build_tables(prob, hc.tables, hc.stream)) return rc;
-    hc.tables_for = *prob;
+  {
+    std::lock_guard<std::mutex> lock(hc.mu);
+    const size_t tb = scp_b200_tables_bytes(prob);
+    if (!hc.tables_valid || tb != hc.tables_bytes || memcmp(&hc.tables_for, prob, sizeof(*prob)) != 0) {
+      // the other lane may still be reading the old tables: build the new ones in a fresh allocation and leave the old
+      // one to be freed when it is replaced the next time (a problem change between calls is rare)
+      std::vector<void*>& retired = hc.retired;
+      void* fresh = nullptr;
+      CUDA_OK(cudaMalloc(&fresh, tb));
+      if (int rc = scp_b200_build_tables(prob, fresh, ln.stream)) { cudaFree(fresh); return rc; }
+      if (hc.tables) retired.push_back(hc.tables);
+      while (retired.size() > 2) { cudaFree(retired.front()); retired.erase(retired.begin()); }
+      hc.tables = fresh; hc.tables_bytes = tb; hc.tables_for = *prob; hc.tables_valid = true;
+    }
   }
+  void* tables = hc.tables;
   int slots = scp_b200_default_slots(prob);
   if (slots > B) slots = B;
   const size_t wb = scp_b200_workspace_bytes(prob, slots);
-  if (wb > hc.ws_bytes) { if (hc.ws) cudaFree(hc.ws); CUDA_OK(cudaMalloc(&hc.ws, wb)); hc.ws_bytes = wb; }
+  if (wb > ln.ws_bytes) { if (ln.ws) cudaFree(ln.ws); ln.ws = nullptr; ln.ws_bytes = 0; CUDA_OK(cudaMalloc(&ln.ws, wb)); ln.ws_bytes = wb; }
   const size_t n2 = (size_t)B * N * 2 * sizeof(double), n3 = (size_t)B * N * K * 2 * sizeof(double);
   const size_t nr = (size_t)B * sizeof(scp_b200_record);
   const size_t iob = 4 * n2 + 3 * n3 + nr + 1024;
-  if (iob > hc.io_bytes) { if (hc.io) cudaFree(hc.io); CUDA_OK(cudaMalloc(&hc.io, iob)); hc.io_bytes = iob; }
-  char* io = (char*)hc.io;
+  if (iob > ln.io_bytes) { if (ln.io) cudaFree(ln.io); ln.io = nullptr; ln.io_bytes = 0; CUDA_OK(cudaMalloc(&ln.io, iob)); ln.io_bytes = iob; }
+  char* io = (char*)ln.io;
   double *d_p0 = (double*)io, *d_v0 = (double*)(io + n2), *d_pf = (double*)(io + 2 * n2), *d_vf = (double*)(io + 3 * n2);
   double *d_acc = (double*)(io + 4 * n2), *d_pos = (double*)(io + 4 * n2 + n3), *d_vel = (double*)(io + 4 * n2 + 2 * n3);
   scp_b200_record* d_rec = (scp_b200_record*)(io + 4 * n2 + 3 * n3);
-  cudaStream_t st = hc.stream;
+  cudaStream_t st = ln.stream;
   CUDA_OK(cudaMemcpyAsync(d_p0, h_p0, n2, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(d_v0, h_v0, n2, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(d_pf, h_pf, n2, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(d_vf, h_vf, n2, cudaMemcpyHostToDevice, st));
-  if (int rc = scp_b200_solve_batch(prob, B, d_p0, d_v0, d_pf, d_vf, hc.tables, hc.ws, hc.ws_bytes, slots, d_acc,
+  if (int rc = scp_b200_solve_batch(prob, B, d_p0, d_v0, d_pf, d_vf, tables, ln.ws, ln.ws_bytes, slots, d_acc,
                                     d_pos, d_vel, d_rec, st))
     return rc;
   if (h_acc) CUDA_OK(cudaMemcpyAsync(h_acc, d_acc, n3, cudaMemcpyDeviceToHost, st));

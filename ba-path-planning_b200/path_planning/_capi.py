@@ -105,6 +105,7 @@ _SIGNATURES = {
     "scp_b200_last_error": (C.c_char_p, []),
     "scp_b200_sizeof_problem": (C.c_size_t, []),
     "scp_b200_sizeof_record": (C.c_size_t, []),
+    "scp_b200_measure_fp64_peak": (C.c_int, [_P(C.c_double)]),
     "scp_b200_default_problem": (None, [_P(Problem), C.c_int, C.c_double, C.c_double, C.c_double]),
     "scp_b200_tables_bytes": (C.c_size_t, [_P(Problem)]),
     "scp_b200_build_tables": (C.c_int, [_P(Problem), C.c_void_p, C.c_void_p]),

@@ -43,22 +43,24 @@ class BatchSolver:
             _capi.check(self.lib.scp_b200_build_tables(C.byref(self.problem), self.tables.data_ptr(),
                                                        torch.cuda.current_stream(self.device).cuda_stream))
             self.max_slots = int(self.lib.scp_b200_default_slots(C.byref(self.problem)))
-        self._ws = None
-        self._ws_slots = 0
+        self._ws = {}          # lane -> (workspace tensor, slots)
 
-    def _workspace(self, slots):
+    def _workspace(self, slots, lane=0):
         import torch
 
-        if self._ws is None or slots > self._ws_slots:
+        ws, have = self._ws.get(lane, (None, 0))
+        if ws is None or slots > have:
             nbytes = self.lib.scp_b200_workspace_bytes(C.byref(self.problem), slots)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._ws_slots = slots
-        return self._ws
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[lane] = (ws, slots)
+        return ws
 
-    def solve_device(self, p0, pf, v0=None, vf=None):
+    def solve_device(self, p0, pf, v0=None, vf=None, lane=0):
         """p0, pf (and optional v0, vf): float64 CUDA tensors (B,N,2).  Returns device tensors
         acc,pos,vel (B,N,K,2) and a uint8 tensor holding B result records; asynchronous on
-        the current stream."""
+        the current stream.  `lane` selects the workspace: batches issued on different streams with different
+        lanes run concurrently (the solver's CTAs retire as their queue drains, so the tail of one batch -- a few long
+        scenarios -- overlaps the head of the next)."""
         import torch
 
         B = p0.shape[0]
@@ -72,7 +74,7 @@ class BatchSolver:
         out = torch.empty((3, B, self.N, self.K, 2), dtype=torch.float64, device=self.device)
         rec = torch.empty(B * C.sizeof(_capi.Record), dtype=torch.uint8, device=self.device)
         slots = min(self.max_slots, B)
-        ws = self._workspace(slots)
+        ws = self._workspace(slots, lane)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
             _capi.check(self.lib.scp_b200_solve_batch(

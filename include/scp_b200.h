@@ -116,6 +116,10 @@ size_t scp_b200_sizeof_problem(void);
 size_t scp_b200_sizeof_record(void);
 const char* scp_b200_last_error(void);
 
+/* Measurement aid (bench.py): sustained fp64 FMA throughput of the current device in TFLOP/s -- the roofline
+ * denominator of the solver kernels, whose arithmetic is fp64 on the FMA pipe (the reference computes in numpy float64). */
+int scp_b200_measure_fp64_peak(double* tflops_out);
+
 /* Fill `prob` with the reference's defaults (scp.py:32-74, OSQP-free settings). */
 void scp_b200_default_problem(scp_b200_problem* prob, int n_agents, double time_horizon,
                               double time_step, double min_distance);

@@ -32,11 +32,36 @@ CASES = [  # name, N, T, h, R, space, seed (None: explicit positions)
     ("n15_s2", 15, 10.0, 0.2, 0.8, [0, 0, 20, 20], 2),
     ("n25_s3", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 3),
     ("n25_s10003", 25, 10.0, 0.2, 0.8, [0, 0, 20, 20], 10003),
+    # round 2: BASELINE.json config 1 sized (compute-trajectories defaults: 10 agents, T=100, h=0.2 -> K=500, 200 x 200 m)
+    ("n10_k500_s0", 10, 100.0, 0.2, 0.8, [0, 0, 200, 200], 0),
+    # 50 agents (config-5 size); the first seed whose subproblems all certify
+    ("n50_s1", 50, 10.0, 0.2, 0.8, [0, 0, 20, 20], 1),
 ]
+# Cases in which a BOX row class binds at the optimum (the reference's limits are plain attributes set in
+# SCP.__init__, scp.py:67-74, read by _precompute_constraint_matrices, scp.py:188-257): name -> overrides.
+#   acc / jerk: limits lowered until the min-energy manoeuvre saturates them; pos: arena tightened around the straight
+#   paths so that the evasive detour hits the wall.
+EXTRA = {
+    "n5_s0_acc": dict(base="n5_s0", acc=0.6),      # unconstrained optimum has max |a| = 0.79
+    "n5_s0_jerk": dict(base="n5_s0", jerk=0.12),   # ... and max |jerk| = 0.165
+    # two agents swapping places along y = 1.0 / 1.1 in a corridor: the lower wall (0.8) stops agent 0's detour after
+    # 0.2 m, so its position rows bind while agent 1 takes the rest of the 0.8 m separation
+    "n2_corridor_pos": dict(N=2, T=10.0, h=0.2, R=0.8, space=[0.0, 0.8, 10.0, 1.9],
+                            p0=[[1.0, 1.0], [9.0, 1.1]], pf=[[9.0, 1.0], [1.0, 1.1]]),
+}
+CASES += [(k, None, None, None, None, None, None) for k in EXTRA]
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(ref, N, T, h, R, space, p0, pf, overrides):
+def apply_limits(s, limits):
+    """Box limits are attributes of the reference's SCP object (scp.py:67-74)."""
+    for key, names in (("vel", ("vel_min", "vel_max")), ("acc", ("acc_min", "acc_max")), ("jerk", ("jerk_min", "jerk_max"))):
+        if limits and key in limits:
+            setattr(s, names[0], -float(limits[key]))
+            setattr(s, names[1], float(limits[key]))
+
+
+def run_reference(ref, N, T, h, R, space, p0, pf, overrides, limits=None):
     import osqp
 
     osqp.OVERRIDES.clear()
@@ -44,6 +69,7 @@ def run_reference(ref, N, T, h, R, space, p0, pf, overrides):
     osqp.STATS.clear()
     with ref_loader.quiet() as buf:
         s = ref.solvers.scp.SCP(n_vehicles=N, time_horizon=T, time_step=h, min_distance=R, space_dims=space)
+        apply_limits(s, limits)
         s.set_initial_states(p0)
         s.set_final_states(pf)
         tr = s.generate_trajectories(max_iterations=15)
@@ -57,6 +83,16 @@ def main(only=None):
     ref = ref_loader.load_reference()
     gen = ref.scenarios.position_generator.generate_positions
     for name, N, T, h, R, space, seed in CASES:
+        limits, explicit = None, None
+        if name in EXTRA:
+            ex = EXTRA[name]
+            if "base" in ex:
+                base = [c for c in CASES if c[0] == ex["base"]][0]
+                _, N, T, h, R, space, seed = base
+            else:
+                N, T, h, R, space, seed = ex["N"], ex["T"], ex["h"], ex["R"], ex["space"], -1
+                explicit = (np.array(ex["p0"], float), np.array(ex["pf"], float))
+            limits = {k: ex[k] for k in ("vel", "acc", "jerk") if k in ex}
         # the certificate, not the ADMM tolerance, makes the result exact; larger cases start the refinement earlier
         eps = 1e-5 if N < 15 else 1e-3
         truth = dict(eps_abs=eps, eps_rel=eps, max_iter=200000, certify=True)
@@ -68,20 +104,25 @@ def main(only=None):
         t0 = time.time()
         random.seed(seed)
         np.random.seed(seed)
-        p0, pf = gen(N, R)
-        tr, rels, stats = run_reference(ref, N, T, h, R, space, p0, pf, truth)
+        p0, pf = explicit if explicit is not None else gen(N, R)
+        tr, rels, stats = run_reference(ref, N, T, h, R, space, p0, pf, truth, limits)
         certs = [s["cert"] for s in stats]
-        assert all(s["polish"] == 1 and s["cert"] <= 1e-9 for s in stats), (name, certs)
+        if not all(s["polish"] == 1 and s["cert"] <= 1e-9 for s in stats):
+            print(f"{name}: REJECTED (a subproblem did not certify: {certs})", flush=True)
+            continue
         osqp = scp_oracle._osqp()
         osqp.OVERRIDES.update(truth)
         o = scp_oracle.ScpOracle(N, T, h, R, space)
+        apply_limits(o, limits)
         o.set_initial_states(p0)
         o.set_final_states(pf)
         tro = o.generate_trajectories(15)
         osqp.OVERRIDES.clear()
         for k in ("positions", "velocities", "accelerations"):
             assert np.abs(tr[k] - tro[k]).max() <= 1e-9, (name, k)
-        loose, rels_loose, _ = run_reference(ref, N, T, h, R, space, p0, pf, {})
+        loose, rels_loose, _ = run_reference(ref, N, T, h, R, space, p0, pf, {}, limits)
+        lim = dict(vel=2.0, acc=15.0, jerk=20.0)
+        lim.update(limits or {})
         np.savez_compressed(
             path, N=N, T=T, h=h, R=R, space=np.array(space, float), seed=seed, p0=p0, pf=pf,
             positions=tr["positions"], velocities=tr["velocities"], accelerations=tr["accelerations"],
@@ -90,6 +131,7 @@ def main(only=None):
             objective=float((tr["accelerations"] ** 2).sum()), min_separation=scp_oracle.min_separation(tr["positions"]),
             loose_positions=loose["positions"], loose_accelerations=loose["accelerations"],
             loose_rel_steps=np.array(rels_loose),
+            vel_limit=lim["vel"], acc_limit=lim["acc"], jerk_limit=lim["jerk"],
         )
         print(f"{name}: {len(rels)} SCP iterations, max cert {max(certs):.1e}, {time.time()-t0:.0f}s", flush=True)
 
