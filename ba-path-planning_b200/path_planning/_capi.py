@@ -14,7 +14,8 @@ MAX_SCP_ITER = 32
 ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libscp_b200.so")
+# in-tree build (csrc/Makefile -> ../lib); an installed package points SCP_B200_LIB at its copy
+LIB_PATH = os.environ.get("SCP_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libscp_b200.so")
 
 
 class Problem(C.Structure):

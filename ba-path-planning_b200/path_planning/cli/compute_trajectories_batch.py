@@ -4,16 +4,25 @@ src/path_planning/cli/compute_trajectories_batch.py:14-173).  Same CONFIG keys, 
 N,trial_index,status,time_sec,K,T,h,error); fields are only added.
 
 New: with ``CONFIG["batched"]`` (default True) all trials of one N are solved by ONE device
-launch (scenario-level data parallelism), optionally sharded over the ranks of a
-torch.distributed job; ``time_sec`` of a batched trial is the batch wall time / trials and
-``batch_time_sec`` holds the batch wall time.  ``CONFIG["rng_seed"]`` now seeds the stdlib
-``random`` module that the scenario generator really uses (the reference's np.random.seed does
-not reach it -- TODOs at compute_trajectories_batch.py:40,65); the seed is stored per run.
+launch (scenario-level data parallelism).  ``time_sec`` keeps the reference's meaning -- the time
+of THAT trial's solve (compute_trajectories_batch.py:46-55): it is the GPU time the scenario
+itself occupied (``device_ns`` of its result record) plus its share of the host<->device copies,
+so trials of one N keep their spread for the box-plot consumer; ``batch_time_sec`` (added) is the
+wall time of the whole launch.  Launched under ``torch.distributed.run`` (WORLD_SIZE > 1) the
+trials of every N are sharded over the ranks, one GPU each, with no data-path collective
+(solvers/sharding.py); rank 0 gathers the records and writes the files.  ``CONFIG["rng_seed"]``
+now seeds the stdlib ``random`` module that the scenario generator really uses (the reference's
+np.random.seed does not reach it -- TODOs at compute_trajectories_batch.py:40,65); the seed is
+stored per run.  A YAML file with the same keys (``compute-trajectories-batch config.yaml`` or
+the SCP_BATCH_CONFIG environment variable; reference TODO at :12 and configs/info.txt) overrides
+CONFIG; see configs/batch_default.yaml.
 """
 
 import csv
 import json
+import os
 import random
+import sys
 import time
 from datetime import datetime
 from pathlib import Path
@@ -61,10 +70,44 @@ def run_single_trial(N, cfg, rng):
     }
 
 
-def run_batch(N, cfg, n_trials, seeds=None):
-    """All trials of one N in one device launch.  Returns the list of per-trial records."""
-    from ..solvers.batch import BatchSolver
+def load_config(path):
+    """YAML file -> dict of CONFIG overrides (unknown keys are rejected; reference TODO, :12)."""
+    import yaml
 
+    with open(path, "r", encoding="utf-8") as f:
+        data = yaml.safe_load(f) or {}
+    if not isinstance(data, dict):
+        raise ValueError(f"{path}: expected a mapping of CONFIG keys")
+    unknown = sorted(set(data) - set(CONFIG) - {"engine"})
+    if unknown:
+        raise ValueError(f"{path}: unknown config keys {unknown}; known: {sorted(CONFIG)}")
+    return data
+
+
+def _dist_context():
+    """(rank, world) of a torch.distributed.run launch; initialises the process group (gloo: only result records
+    travel) and binds this process to its GPU.  (0, 1) when launched plainly."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+    return dist.get_rank(), dist.get_world_size()
+
+
+def run_batch(N, cfg, n_trials, seeds=None):
+    """All trials of one N in one device launch per rank.  Returns the list of per-trial records (every rank
+    receives all of them; trials are sharded over the ranks of a torch.distributed job)."""
+    from ..solvers.batch import BatchSolver
+    from ..solvers.sharding import gather_records, shard_range
+
+    rank, world = _dist_context()
     starts, goals, used = [], [], []
     for t in range(n_trials):
         if seeds is not None:
@@ -73,6 +116,11 @@ def run_batch(N, cfg, n_trials, seeds=None):
         starts.append(p0)
         goals.append(pf)
         used.append(None if seeds is None else seeds[t])
+    lo, hi = shard_range(n_trials, rank, world)
+    if hi <= lo:
+        return gather_records([])
+    n_trials = hi - lo
+    starts, goals, used = starts[lo:hi], goals[lo:hi], used[lo:hi]
     from ..solvers.scp import use_stream_engine
 
     K = int(cfg["time_horizon"] / cfg["time_step"])
@@ -87,17 +135,22 @@ def run_batch(N, cfg, n_trials, seeds=None):
     t0 = time.perf_counter()
     _, recs = solver.solve(np.stack(starts), np.stack(goals))
     dt = time.perf_counter() - t0
+    # copies of one trial: 4 (N,2) inputs up, 3 (N,K,2) outputs + the record down, at the PCIe rate the batch saw
+    # (bounded by what is left of the wall time after the longest scenario)
+    longest = max(r["device_ns"] for r in recs) * 1e-9
+    copy_share = max(0.0, dt - longest) / n_trials
     out = []
     for t, r in enumerate(recs):
         failed = r["status"] == 1
         out.append({
-            "N": N, "status": "error" if failed else "success", "time_sec": dt / n_trials,
+            "N": N, "status": "error" if failed else "success", "time_sec": r["device_ns"] * 1e-9 + copy_share,
             "error": "OSQP failed: initial QP not solved" if failed else None,
-            "K": solver.K, "T": cfg["time_horizon"], "h": cfg["time_step"], "trial_index": t,
-            "batch_time_sec": dt, "seed": used[t], "scp_iterations": r["scp_iterations"],
-            "admm_iterations": r["admm_iterations"], "min_separation": r["min_separation"],
+            "K": solver.K, "T": cfg["time_horizon"], "h": cfg["time_step"], "trial_index": lo + t,
+            "batch_time_sec": dt, "device_time_sec": r["device_ns"] * 1e-9, "seed": used[t], "rank": rank,
+            "scp_iterations": r["scp_iterations"], "admm_iterations": r["admm_iterations"],
+            "qp_unsolved": r["qp_unsolved"], "min_separation": r["min_separation"],
         })
-    return out
+    return gather_records(out) if world > 1 else out
 
 
 def summarize(runs, Ns):
@@ -120,8 +173,23 @@ def summarize(runs, Ns):
 
 def main(config=None):
     cfg = CONFIG.copy()
+    yaml_path = os.environ.get("SCP_BATCH_CONFIG")
+    if config is None and len(sys.argv) > 1 and sys.argv[1].endswith((".yaml", ".yml")):
+        yaml_path = sys.argv[1]
+    if yaml_path:
+        cfg.update(load_config(yaml_path))
     if config:
         cfg.update(config)
+    rank, world = _dist_context()
+    if world > 1 and not cfg.get("batched", True):
+        raise ValueError("a torch.distributed launch shards batched trials: set batched: true")
+    if rank != 0:                       # the other ranks only solve their shard of every N
+        for N in cfg["Ns"]:
+            seeds = None
+            if cfg["rng_seed"] is not None:
+                seeds = [cfg["rng_seed"] + 1000 * N + t for t in range(cfg["trials_per_N"])]
+            run_batch(N, cfg, cfg["trials_per_N"], seeds)
+        return None
     Path(cfg["results_dir"]).mkdir(parents=True, exist_ok=True)
     stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
     json_path = Path(cfg["results_dir"]) / f"scp_benchmark_{stamp}.json"

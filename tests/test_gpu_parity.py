@@ -7,12 +7,13 @@ dynamics-residual check (<= 1e-3).  Index/ordering work (row order
 violation) is compared exactly; fp64 kernels that restate closed-form maps to 1e-12.
 """
 import ctypes as C
+import os
 import random
 
 import numpy as np
 import pytest
 
-from conftest import golden_cases
+from conftest import GOLDEN, active_box_classes, golden_cases, golden_limits
 
 pytestmark = pytest.mark.gpu
 
@@ -161,7 +162,8 @@ def test_solve_matches_golden(torch_cuda, lib, path):
 
     g = np.load(path)
     N, h, R, space = int(g["N"]), float(g["h"]), float(g["R"]), list(g["space"])
-    acc, pos, vel, recs = _solve_host(lib, g["p0"], g["pf"], float(g["T"]), h, R, space)
+    lim = golden_limits(g)
+    acc, pos, vel, recs = _solve_host(lib, g["p0"], g["pf"], float(g["T"]), h, R, space, **lim)
     r = recs[0]
     assert r["status"] == 0 and r["qp_unsolved"] == 0
     assert r["scp_iterations"] == int(g["iterations"])
@@ -175,8 +177,18 @@ def test_solve_matches_golden(torch_cuda, lib, path):
     # same pass/fail on the two feasibility checks
     assert (r["min_separation"] >= R - 0.01) == (float(g["min_separation"]) >= R - 0.01)
     assert abs(r["min_separation"] - scp_oracle.min_separation(pos[0])) <= 1e-12
-    dyn = scp_oracle.dynamics_residual(acc[0], g["p0"], z, g["pf"], z, h, space, positions=pos[0])
+    dyn = scp_oracle.dynamics_residual(acc[0], g["p0"], z, g["pf"], z, h, space, positions=pos[0],
+                                       vlim=lim.get("vel_limit", 2.0), alim=lim.get("acc_limit", 15.0),
+                                       jlim=lim.get("jerk_limit", 20.0))
     assert dyn <= DYN_TOL
+    # the box classes that bind at the reference's optimum bind here too (cases *_acc, *_jerk, *_pos; vel binds in several)
+    got = dict(np.load(path))
+    got.update(accelerations=acc[0], velocities=vel[0], positions=pos[0])
+
+    class _G(dict):
+        files = list(got)
+
+    assert active_box_classes(_G(got), tol=1e-5) == active_box_classes(g, tol=1e-5)
     # the loose (eps 1e-3) reference itself sits further from the minimiser than we do
     loose = np.linalg.norm(g["loose_positions"] - g["positions"]) / np.linalg.norm(g["positions"])
     print(f"{path.split('/')[-1]}: pos err {perr:.1e} (loose reference {loose:.1e}), objective err {oerr:.1e}, "
@@ -286,6 +298,66 @@ def test_start_too_close_is_flagged(torch_cuda, lib):
     pf = np.array([[15.0, 5.0], [15.0, 8.0]])
     _, _, _, recs = _solve_host(lib, p0, pf, 10.0, 0.2, 0.8, [0, 0, 20, 20], max_admm_iter=2000)
     assert recs[0]["status"] == 2 and recs[0]["first_violation"] == (0, 0, 1)
+
+
+def test_golden_set_covers_binding_box_rows_and_config_sizes():
+    """the fixtures include a K=500 config-1 case, a 50-agent case and, per box class, a case where
+    that class binds at the certified optimum."""
+    names = [os.path.basename(p) for p in golden_cases()]
+    active = set()
+    for p in golden_cases():
+        active |= active_box_classes(np.load(p), tol=1e-6)
+    assert {"jerk", "acc", "vel", "pos"} <= active, active
+    assert any(int(np.load(p)["N"]) >= 50 for p in golden_cases()), names
+    assert any(round(float(np.load(p)["T"]) / float(np.load(p)["h"])) >= 500 for p in golden_cases()), names
+
+
+def test_c2_reference_outcomes_fixture(torch_cuda, lib):
+    """The benchmark's own scenarios (config 2, seeds 10000..10063) against the outcomes of the VERBATIM reference at its
+    own solver settings (tests/golden/c2_outcomes.npz, oracle/make_outcomes.py: OSQP defaults eps 1e-3, max_iter 10000,
+    scp.py:360,442).  Unlike the n*.npz fixtures these are NOT filtered: 27 of the 64 contain a subproblem the
+    reference ends as 'solved inaccurate' or at max_iter (scp.py:446-449: warning, iterate kept).
+
+    Contract checked here:
+      * same batch status ("success" on both sides for all 64, compute_trajectories_batch.py:50-54), finite
+        trajectories, same pass on the dynamics-residual check (<= 1e-3);
+      * minimum separation: the device result passes scp.py:610's R - 0.01 everywhere; the reference's eps-1e-3
+        iterates sit up to its own primal tolerance (1e-3 (1 + 20 m)) below R, so its pass/fail is compared within
+        that tolerance;
+      * scenarios whose subproblems all solve on both sides: positions within 1e-2 relative of the LOOSE reference
+        (median <= 2e-3) -- the loose reference is itself ~1e-3 from its own re-run (c2_outcomes_alt.npz) and
+        3e-4..9e-4 from the certified minimiser the device path reproduces to 1e-12 (test_solve_matches_golden);
+      * scenarios with an unsolved subproblem have no defined minimiser: trajectories are solver dependent on both
+        sides, only bounded here (<= 5e-2 relative)."""
+    from oracle import scp_oracle
+
+    f = np.load(os.path.join(GOLDEN, "c2_outcomes.npz"))
+    n, R, h, space = len(f["seed"]), 0.8, 0.2, [0, 0, 20, 20]
+    acc, pos, vel, recs = _solve_host(lib, f["p0"], f["pf"], 10.0, h, R, space)
+    z = np.zeros((25, 2))
+    qs = f["qp_status"]
+    ref_solved = np.array([(qs[b, : f["n_qp"][b]] == 1).all() for b in range(n)])
+    gpu_solved = np.array([recs[b]["qp_unsolved"] == 0 for b in range(n)])
+    slack = 1e-3 * (1 + 20.0)
+    pe = np.empty(n)
+    for b in range(n):
+        assert (recs[b]["status"] == 0) == (str(f["status"][b]) == "success"), b
+        assert np.isfinite(pos[b]).all() and np.isfinite(acc[b]).all() and bool(f["finite"][b])
+        dyn = scp_oracle.dynamics_residual(acc[b], f["p0"][b], z, f["pf"][b], z, h, space, positions=pos[b])
+        assert (dyn <= DYN_TOL) == bool(f["dyn_pass"][b]), (b, dyn)
+        assert recs[b]["min_separation"] >= R - 0.01, (b, recs[b]["min_separation"])
+        pe[b] = np.linalg.norm(pos[b] - f["positions"][b]) / np.linalg.norm(f["positions"][b])
+    ref_sep_ok = f["min_separation"] >= R - 0.01 - slack
+    assert ref_sep_ok.sum() >= n - 12, int(ref_sep_ok.sum())       # the rest: reference iterates beyond its own tolerance
+    both = ref_solved & gpu_solved
+    assert both.sum() >= 28 and (~ref_solved).sum() >= 20          # the fixture really contains both kinds
+    assert pe[both].max() <= 1e-2 and np.median(pe[both]) <= 2e-3, (pe[both].max(), np.median(pe[both]))
+    assert pe[~both].max() <= 5e-2, pe[~both].max()
+    dscp = np.abs(np.array([recs[b]["scp_iterations"] for b in range(n)]) - f["scp_iterations"])
+    assert dscp[both].max() <= 3
+    assert abs(int((~gpu_solved).sum()) - int((~ref_solved).sum())) <= 8
+    print(f"c2 outcomes: {int(both.sum())} scenarios solved on both sides, pos err median {np.median(pe[both]):.1e} max "
+          f"{pe[both].max():.1e}; {int((~both).sum())} with an unsolved subproblem, pos err median {np.median(pe[~both]):.1e}")
 
 
 # ------------------------------------------------------------------ BASELINE.json config sizes: properties

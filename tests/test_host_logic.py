@@ -165,3 +165,106 @@ def test_stream_solver_has_no_cpu_path():
 
     with pytest.raises(_capi.ScpB200Error):
         StreamSolver(5, 10.0, 0.2, 0.8)
+
+
+# ------------------------------------------------------------------ batch CLI: YAML config, rank sharding, time_sec
+def test_yaml_config_loader(tmp_path):
+    cfgs = os.path.join(os.path.dirname(ctb.__file__), "..", "configs")
+    c = ctb.load_config(os.path.join(cfgs, "batch_default.yaml"))
+    assert c == {k: ctb.CONFIG[k] for k in c} and set(c) == set(ctb.CONFIG)        # the default file IS the CONFIG dict
+    c2 = ctb.load_config(os.path.join(cfgs, "config2_1024x25.yaml"))
+    assert c2["Ns"] == [25] and c2["trials_per_N"] == 1024
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("trials: 3\n")
+    with pytest.raises(ValueError):
+        ctb.load_config(str(bad))
+
+
+class _FakeBatchSolver:
+    """Stands in for BatchSolver on a machine without a GPU: scenario b 'costs' (1 + b) ms of device time."""
+
+    def __init__(self, N, T, h, R, space, **kw):
+        self.K = int(T / h)
+
+    def solve(self, p0, pf):
+        recs = [dict(status=0, device_ns=int(1e6 * (1 + p0[b, 0, 0])), scp_iterations=3, admm_iterations=100,
+                     qp_unsolved=0, min_separation=0.8) for b in range(len(p0))]
+        return {}, recs
+
+
+def _cli_worker(rank, world, port, results_dir, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import path_planning.solvers.batch as batch
+    from path_planning.cli import compute_trajectories_batch as c
+
+    batch.BatchSolver = _FakeBatchSolver
+    c.generate_positions = lambda N, R: (np.full((N, 2), float(c.random.random())), np.zeros((N, 2)))
+    out = c.main({"Ns": [4], "trials_per_N": 5, "rng_seed": 7, "results_dir": results_dir, "engine": "cta"})
+    q.put((rank, None if out is None else [(r["trial_index"], r["rank"], r["seed"], r["time_sec"], r["batch_time_sec"]) for r in out["runs"]]))
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+
+
+def test_batch_cli_shards_trials_over_ranks_gloo(tmp_path):
+    """compute-trajectories-batch under a 2-rank launch: each rank solves its shard of the trials, rank 0 gathers all
+    records and writes the files; time_sec is per trial (device time of that scenario + copy share), not batch/trials."""
+    import glob
+    import json
+
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_cli_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res[1] is None                                   # only rank 0 reports / writes
+    runs = res[0]
+    assert [r[0] for r in runs] == [0, 1, 2, 3, 4] and [r[1] for r in runs] == [0, 0, 0, 1, 1]
+    assert [r[2] for r in runs] == [7 + 4000 + t for t in range(5)]
+    times = [r[3] for r in runs]
+    assert len(set(round(t, 9) for t in times)) > 1         # spread kept: not batch wall / trials
+    assert all(0 < t <= r[4] + 1e-3 + 2e-3 for t, r in zip(times, runs))
+    files = glob.glob(str(tmp_path / "scp_benchmark_*.json"))
+    assert len(files) == 1
+    data = json.load(open(files[0]))
+    assert len(data["runs"]) == 5 and data["summary"]["4"]["count"] == 5 and data["meta"]["schema_version"] == "1.0"
+
+
+def test_bench_parity_block_on_the_fixture_itself():
+    """bench.py's parity bookkeeping, fed with the reference's own outcomes as if they were the device's: every
+    confusion matrix is diagonal and every error is zero."""
+    import importlib.util
+
+    from conftest import GOLDEN, ROOT
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = np.load(os.path.join(GOLDEN, "c2_outcomes.npz"))
+    n = 12
+    qs = f["qp_status"]
+    recs = [dict(status=0, qp_unsolved=int((qs[b, : f["n_qp"][b]] != 1).sum()), objective=float(f["objective"][b]),
+                 scp_iterations=int(f["scp_iterations"][b])) for b in range(n)]
+    w = bench.WORKLOADS["c2"]
+    out = bench.parity_block(w, recs, f["accelerations"][:n], f["positions"][:n], f["p0"][:n], f["pf"][:n])
+    assert out["scenarios"] == n and out["status"]["both_success"] == n
+    for key in ("finite_trajectory", "dynamics_residual_pass_1e-3", "min_separation_pass_R-0.01"):
+        assert out[key]["ref_pass_gpu_fail"] == 0 and out[key]["ref_fail_gpu_pass"] == 0, (key, out[key])
+    assert out["both_all_solved"]["position_rel_err"]["max"] == 0.0
+    assert out["scp_iterations_equal"]["all"] == n
+    assert out["subproblems"]["both_all_solved"] + out["subproblems"]["both_unsolved"] == n
+    # the bench's own restatement of the two feasibility checks agrees with the oracle's
+    from oracle import scp_oracle
+
+    z = np.zeros((25, 2))
+    for b in range(3):
+        a, p = f["accelerations"][b], f["positions"][b]
+        assert abs(bench.dynamics_residual(a, p, f["p0"][b], f["pf"][b], 0.2, [0, 0, 20, 20])
+                   - scp_oracle.dynamics_residual(a, f["p0"][b], z, f["pf"][b], z, 0.2, [0, 0, 20, 20], positions=p)) <= 1e-12
+        assert abs(bench.min_separation(p) - scp_oracle.min_separation(p)) <= 1e-15
