@@ -51,16 +51,25 @@ size_t nmat_smem_bytes(int K) {
   return b <= SMEM_NMAT_LIMIT ? b : 0;
 }
 
-// Shared-memory plan of scp_solve_kernel: base scratch, the K x K operator when it fits, the per-warp rows of
-// the fused iteration (K <= 64), then as many hot per-agent-axis arrays as fit, in order of reuse
-// (P and F are also read by the collision rows, then x and the four v arrays, rhs last).
+// Shared-memory plan of scp_solve_kernel: base scratch, the K x K operator when it fits, the scratch rows of the fused
+// iteration (K <= 64), then as many hot per-agent-axis arrays as fit, in order of reuse (P and F are also read by the
+// collision rows, then x and the four v arrays, rhs last).  When all eight fit (config 2) the iteration runs its
+// operator product on the tensor pipe (admm_iter_mma); otherwise the warp-fused iteration keeps the product's
+// operands in registers (measured at 50 / 100 agents: faster than staging rhs and x through L2).
+size_t fused_scratch_doubles(int N, int K) {
+  size_t a = (size_t)(SOLVE_THREADS / 32) * K, b = (size_t)2 * K + (size_t)4 * N;   // old per-warp rows | N0 (2K) + d (4N)
+  return ((a > b ? a : b) + 1) & ~(size_t)1;
+}
 size_t plan_smem(int N, int K, int* hot_mask) {
   size_t smem = SMEM_BASE + nmat_smem_bytes(K);
-  if (nmat_smem_bytes(K) && K <= 64) smem += (size_t)(SOLVE_THREADS / 32) * K * sizeof(double);
+  const bool fused = nmat_smem_bytes(K) && K <= 64;
+  if (fused) smem += fused_scratch_doubles(N, K) * sizeof(double);
   const size_t arr = (size_t)2 * N * K * sizeof(double);
   int mask = 0;
-  for (int a = 0; a < 8; ++a)
+  for (int o = 0; o < 8; ++o) {
+    const int a = o;                                     // array index in {P, F, x, vp, vv, vj, va, rhs}
     if (smem + arr <= SMEM_TOTAL_LIMIT) { smem += arr; mask |= 1 << a; }
+  }
   if (hot_mask) *hot_mask = mask;
   return smem;
 }
@@ -107,12 +116,18 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     double* cur = smem + scp::sh_doubles(scp::RED) + (nmat_in_smem ? (size_t)c.K * c.K : 0);
     c.fused_rows = cur;
     const int fused_ok = nmat_in_smem && c.K <= 64;
-    if (fused_ok) cur += (size_t)(blockDim.x >> 5) * c.K;
+    if (fused_ok) {
+      const size_t a = (size_t)(blockDim.x >> 5) * c.K, b = (size_t)2 * c.K + (size_t)4 * c.N;
+      cur += ((a > b ? a : b) + 1) & ~(size_t)1;
+    }
     double* glob[8] = {c.wd + g.L.P, c.wd + g.L.F, c.wd + g.L.x, c.wd + g.L.vp, c.wd + g.L.vv, c.wd + g.L.vj, c.wd + g.L.va, c.wd + g.L.rhs};
     double* ptr[8];
-    for (int a = 0; a < 8; ++a) {
+    for (int o = 0; o < 8; ++o) {
+      const int a = o;                                        // same order as plan_smem
       if (hot_mask & (1 << a)) { ptr[a] = cur; cur += QK; } else ptr[a] = glob[a];
     }
+    c.all_hot = (hot_mask & 0xFF) == 0xFF;
+    c.mma_ok = c.all_hot;
     c.a_P = ptr[0]; c.a_F = ptr[1]; c.a_x = ptr[2]; c.a_vp = ptr[3]; c.a_vv = ptr[4]; c.a_vj = ptr[5]; c.a_va = ptr[6]; c.a_rhs = ptr[7];
     c.fused_epl = fused_ok ? 2 : 0;
     // region the polish factors in (hot arrays are assigned contiguously, in this order, rhs last and never parked)
@@ -120,7 +135,7 @@ scp_solve_kernel(const __grid_constant__ scp::Params g, int B, const double* __r
     for (int a = 0; a < 7; ++a) {
       const bool hot = (hot_mask >> a) & 1;
       c.hot_s[a] = hot ? ptr[a] : nullptr; c.hot_g[a] = glob[a];
-      if (hot) { if (!c.pol_smem) c.pol_smem = ptr[a]; c.pol_smem_doubles += QK; }
+      if (hot) { if (!c.pol_smem || ptr[a] < c.pol_smem) c.pol_smem = ptr[a]; c.pol_smem_doubles += QK; }
     }
   }
   // Work queue of quanta (one SCP iteration each).  Fresh scenarios (tickets 0..B-1) come first, so that every scenario
@@ -204,7 +219,7 @@ scp_solve_team_kernel(const __grid_constant__ scp::Params g, int B, const double
   c.wd = ws_d; c.wi = ws_i;
   c.sm = smem;
   c.nmat = nullptr; c.nmat_in_smem = 0;
-  c.fused_epl = 0; c.fused_rows = nullptr;
+  c.fused_epl = 0; c.fused_rows = nullptr; c.all_hot = 0; c.mma_ok = 0;
   c.a_P = c.wd + g.L.P; c.a_F = c.wd + g.L.F; c.a_x = c.wd + g.L.x; c.a_vp = c.wd + g.L.vp;
   c.a_vv = c.wd + g.L.vv; c.a_vj = c.wd + g.L.vj; c.a_va = c.wd + g.L.va; c.a_rhs = c.wd + g.L.rhs;
   c.pol_smem = nullptr; c.pol_smem_doubles = 0;
@@ -496,7 +511,7 @@ int scp_b200_solve_batch(const scp_b200_problem* prob, int B, const double* d_p0
   CUDA_OK(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  const bool team_mode = coop && prob->team_mode != 1 && (prob->team_mode == 2 || (B <= 8 && (size_t)2 * prob->n_agents * K >= 8192));
+  const bool team_mode = coop && prob->team_mode != 1 && prob->team_mode != 3 && (prob->team_mode == 2 || (B <= 8 && (size_t)2 * prob->n_agents * K >= 8192));
   if (team_mode) {
     double* team_scratch = (double*)(base + HEADER_BYTES + slot_bytes(g.L) * (size_t)slots);
     if (scp::sh_doubles((size_t)sms * SOLVE_THREADS) * sizeof(double) > TEAM_SCRATCH_BYTES) return fail(3, "team scratch too small");

@@ -169,7 +169,9 @@ struct Ctx {
   double *acc, *pos, *vel;
   scp_b200_record* rec;
   int fused_epl;                // 0: phase-style iterations only; 2/4: warp-fused iteration with that many steps per lane
-  double* fused_rows;           // per-warp right-hand-side rows (shared)
+  double* fused_rows;           // scratch rows in shared memory (nwarps x K doubles >= 2K + 4N)
+  int all_hot;                  // every hot array lives in shared memory
+  int mma_ok;                   // the tensor-pipe iteration pays (all hot arrays in shared memory)
   // The polish factors its Gram matrix in shared memory: the hot arrays P, F, x, vp, vv, vj, va (everything but rhs)
   // are parked in their global homes for the duration of an attempt and the a_* pointers follow them.
   int pol_no_smem;              // a set outgrew the shared-memory region: later attempts of this scenario use the slot scratch
@@ -182,6 +184,7 @@ struct Ctx {
   int pol_valid, pol_n, pol_use_col, pol_col_stale;   // polish list/inverse state carried between attempts
   long long t_pbuild, t_psolve, t_peval, t_papply;
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
+  long long t_fused, t_colx, t_chk;   // SCP_PROFILE_SPLIT builds only
   // block-uniform solver state
   double rho;
   int copies;
@@ -682,6 +685,195 @@ __device__ __forceinline__ void admm_iter_fused(Ctx& c, double* rhs_rows /* nwar
     }
   }
 }
+
+// ------------------------------------------------------------------ tensor-pipe iteration (GPU only)
+// The same ADMM iteration as admm_iter_fused, organised as three block phases so that the ONE GEMM-shaped contraction
+// of the path -- x = N rhs for all 2N agent-axes of the scenario, [K x K] . [K x 2N] --
+// runs on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA) instead of one broadcast-FMA matvec per warp:
+//   A  one warp per agent-axis: rows -> weighted reflections -> transposed operators -> rhs[q][.]   (shared memory)
+//   B  tiles of 8 steps x 8 agent-axes over the warps, four accumulator tiles in flight per warp: x = N rhs + N0 d
+//   C  one warp per agent-axis: forward rows of the new x, v-updates, new positions
+// Lane L owns the ADJACENT steps 2L, 2L+1 (K <= 64), so a scan over the steps is one local add plus ONE 5-stage warp
+// scan; the double scans S' w and S x are written as two independent first-moment scans (sum w, sum (k+1) w), so the
+// three suffix scans of phase A -- and the two prefix scans of phase C -- advance together instead of one after another.
+// SH: every hot array, the operator and the rhs rows live in shared memory -- they are then indexed off the dynamic
+// shared array so that the compiler emits LDS/STS with 32-bit addresses instead of generic 64-bit loads.
+__device__ __forceinline__ void scp_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool SH>
+struct HotView {     // one hot array: shared-memory offset (SH) or generic pointer
+  double* p; int o;
+  __device__ __forceinline__ HotView(double* base, const double* smem0) : p(base), o(SH ? (int)(base - smem0) : 0) {}
+  __device__ __forceinline__ double ld(int i) const {
+    extern __shared__ double smem[];
+    return SH ? smem[o + i] : p[i];
+  }
+  __device__ __forceinline__ void st(int i, double v) const {
+    extern __shared__ double smem[];
+    if (SH) smem[o + i] = v; else p[i] = v;
+  }
+};
+
+template <bool SH>
+__device__ __forceinline__ void admm_iter_mma(Ctx& c) {
+  extern __shared__ double smem[];
+  const int K = c.K, Q = c.Q, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const double h = c.g->pb.time_step, ih = 1.0 / h, rho = c.rho, sig = c.g->pb.sigma;
+  const double vl = c.g->pb.vel_limit, al = c.g->pb.acc_limit, jl = c.g->pb.jerk_limit;
+  const double cpr = (double)c.copies * rho;
+  const HotView<SH> X(c.a_x, smem), RHS(c.a_rhs, smem), VJ(c.a_vj, smem), VA(c.a_va, smem), VV(c.a_vv, smem),
+      VP(c.a_vp, smem), PP(c.a_P, smem), FF(c.a_F, smem);
+  const HotView<true> NM(const_cast<double*>(c.nmat), smem), SCR(c.fused_rows, smem);   // fused path: always shared
+  const int k0 = 2 * lane, k1 = k0 + 1;
+  const bool in0 = k0 < K, in1 = k1 < K, r0 = k0 < K - 1, r1 = k1 < K - 1;
+  // ---- phase A
+  {
+    // N0 (2K) and d (2Q) for phase B's epilogue: staged in the scratch rows while the warps are busy with the scans
+    const double* N0 = c.wd + c.g->L.N0;
+    const double* deq = c.wd + c.g->L.deq;
+    for (int e = threadIdx.x; e < 2 * K + 2 * Q; e += blockDim.x) SCR.st(e, e < 2 * K ? N0[e] : deq[e - 2 * K]);
+    const double trj0 = r0 ? rho * c.g->tb.rj[k0] : 0.0, trj1 = r1 ? rho * c.g->tb.rj[k1] : 0.0;
+    const double tra0 = in0 ? rho * c.g->tb.ra[k0] : 0.0, tra1 = in1 ? rho * c.g->tb.ra[k1] : 0.0;
+    const double trv0 = r0 ? rho * c.g->tb.rv[k0] : 0.0, trv1 = r1 ? rho * c.g->tb.rv[k1] : 0.0;
+    const double trp0 = r0 ? rho * c.g->tb.rp[k0] : 0.0, trp1 = r1 ? rho * c.g->tb.rp[k1] : 0.0;
+    const double trc0 = r0 ? cpr * c.g->tb.rc[k0] : 0.0, trc1 = r1 ? cpr * c.g->tb.rc[k1] : 0.0;
+    for (int q = warp; q < Q; q += nwarps) {
+      const int b = q * K;
+      const double v0q = c.v0[q], p0q = c.p0[q];
+      const double lv = -vl - v0q, uv = vl - v0q;
+      const double plo = c.g->pb.space[q & 1], phi = c.g->pb.space[2 + (q & 1)];
+      double xo0 = 0, xo1 = 0, wa0 = 0, wa1 = 0, wj0 = 0, wj1 = 0, wv0 = 0, wv1 = 0, wp0 = 0, wp1 = 0;
+      // every v array is overwritten with s = v - z (the scaled multiplier) here; phase C adds the new row to it
+      if (in0) {
+        xo0 = X.ld(b + k0);
+        const double v = VA.ld(b + k0), z = clampd(v, -al, al);
+        wa0 = tra0 * (2 * z - v); VA.st(b + k0, v - z);
+      }
+      if (in1) {
+        xo1 = X.ld(b + k1);
+        const double v = VA.ld(b + k1), z = clampd(v, -al, al);
+        wa1 = tra1 * (2 * z - v); VA.st(b + k1, v - z);
+      }
+      if (r0) {
+        double v = VJ.ld(b + k0), z = clampd(v, -jl, jl); wj0 = trj0 * (2 * z - v); VJ.st(b + k0, v - z);
+        v = VV.ld(b + k0); z = clampd(v, lv, uv); wv0 = trv0 * (2 * z - v); VV.st(b + k0, v - z);
+        const double off = p0q + h * (double)(k0 + 1) * v0q;
+        v = VP.ld(b + k0); z = clampd(v, plo - off, phi - off); VP.st(b + k0, v - z);
+        wp0 = trp0 * (2 * z - v) + trc0 * (PP.ld(b + k0 + 1) - off) + FF.ld(b + k0 + 1);
+      }
+      if (r1) {
+        double v = VJ.ld(b + k1), z = clampd(v, -jl, jl); wj1 = trj1 * (2 * z - v); VJ.st(b + k1, v - z);
+        v = VV.ld(b + k1); z = clampd(v, lv, uv); wv1 = trv1 * (2 * z - v); VV.st(b + k1, v - z);
+        const double off = p0q + h * (double)(k1 + 1) * v0q;
+        v = VP.ld(b + k1); z = clampd(v, plo - off, phi - off); VP.st(b + k1, v - z);
+        wp1 = trp1 * (2 * z - v) + trc1 * (PP.ld(b + k1 + 1) - off) + FF.ld(b + k1 + 1);
+      }
+      // transposed operators: D'wj + wa + V'wv + S'wp; suffix sums of wv, wp and (k+1) wp over the steps
+      double sv = wv0 + wv1, s0 = wp0 + wp1, s1 = (double)(k0 + 1) * wp0 + (double)(k1 + 1) * wp1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double a = __shfl_down_sync(0xffffffffu, sv, d), b0 = __shfl_down_sync(0xffffffffu, s0, d),
+                     b1 = __shfl_down_sync(0xffffffffu, s1, d);
+        if (lane + d < 32) { sv += a; s0 += b0; s1 += b1; }
+      }
+      double pj = __shfl_up_sync(0xffffffffu, wj1, 1);      // wj[k0 - 1]
+      if (lane == 0) pj = 0.0;
+      const double sv1 = sv - wv0, s01 = s0 - wp0, s11 = s1 - (double)(k0 + 1) * wp0;
+      if (in0) RHS.st(b + k0, sig * xo0 + (pj - wj0) * ih + wa0 + h * sv + h * h * (s1 - ((double)k0 + 0.5) * s0));
+      if (in1) RHS.st(b + k1, sig * xo1 + (wj0 - wj1) * ih + wa1 + h * sv1 + h * h * (s11 - ((double)k1 + 0.5) * s01));
+    }
+  }
+  __syncthreads();
+  // ---- phase B: x[q][k] = sum_j N[k][j] rhs[q][j] + N0[k] . d[q] on the fp64 tensor pipe
+  {
+    const int MT = (K + 7) >> 3, NT = (Q + 7) >> 3, total = MT * NT;
+    const int g = lane >> 2, t = lane & 3;
+    for (int tg = warp; tg < total; tg += 4 * nwarps) {
+      int arow[4], brow[4];
+      double c0[4], c1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tile = tg + i * nwarps;
+        const int mt = tile % MT, nt = tile / MT;
+        const int m = mt * 8 + g, n = nt * 8 + g;
+        arow[i] = (tile < total && m < K ? m : K - 1) * K;
+        brow[i] = (tile < total && n < Q ? n : Q - 1) * K;
+        c0[i] = 0.0; c1[i] = 0.0;
+      }
+      // operands of step kk + 4 are fetched before the products of step kk issue
+      double a[4], bb[4];
+      {
+        const int kc = t < K ? t : K - 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = NM.ld(arow[i] + kc); bb[i] = RHS.ld(brow[i] + kc); }
+      }
+      for (int kk = 0; kk < K; kk += 4) {
+        const bool in = kk + t < K;
+        const int kn = kk + 4 + t, kc = kn < K ? kn : K - 1;
+        double a2[4], b2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a2[i] = NM.ld(arow[i] + kc); b2[i] = RHS.ld(brow[i] + kc); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) scp_dmma(c0[i], c1[i], in ? a[i] : 0.0, in ? bb[i] : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = a2[i]; bb[i] = b2[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tile = tg + i * nwarps;
+        if (tile < total) {
+          const int mt = tile % MT, nt = tile / MT;
+          const int k = mt * 8 + g, q = nt * 8 + 2 * t;
+          if (k < K) {
+            const double n0a = SCR.ld(2 * k), n0b = SCR.ld(2 * k + 1);
+            if (q < Q) X.st(q * K + k, c0[i] + n0a * SCR.ld(2 * K + 2 * q) + n0b * SCR.ld(2 * K + 2 * q + 1));
+            if (q + 1 < Q) X.st((q + 1) * K + k, c1[i] + n0a * SCR.ld(2 * K + 2 * q + 2) + n0b * SCR.ld(2 * K + 2 * q + 3));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase C: forward rows of the new x, v <- A x + (v - z), new positions
+  for (int q = warp; q < Q; q += nwarps) {
+    const int b = q * K;
+    const double v0q = c.v0[q], p0q = c.p0[q];
+    const double xn0 = in0 ? X.ld(b + k0) : 0.0, xn1 = in1 ? X.ld(b + k1) : 0.0;
+    double t0 = xn0 + xn1, t1 = (double)k0 * xn0 + (double)k1 * xn1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double a0 = __shfl_up_sync(0xffffffffu, t0, d), a1 = __shfl_up_sync(0xffffffffu, t1, d);
+      if (lane >= d) { t0 += a0; t1 += a1; }
+    }
+    const double nx = __shfl_down_sync(0xffffffffu, xn0, 1);     // x[k1 + 1]
+    // inclusive prefix sums at k1 are (t0, t1); at k0 remove the k1 term
+    const double c10 = t0 - xn1, c11 = t0;
+    const double c20 = (double)(k0 + 1) * c10 - (t1 - (double)k1 * xn1), c21 = (double)(k1 + 1) * c11 - t1;
+    if (in0) {
+      VA.st(b + k0, xn0 + VA.ld(b + k0));
+      if (r0) {
+        const double rv_ = h * c10, rp_ = h * h * (c20 - 0.5 * c10), off = p0q + h * (double)(k0 + 1) * v0q;
+        VJ.st(b + k0, (xn1 - xn0) * ih + VJ.ld(b + k0));
+        VV.st(b + k0, rv_ + VV.ld(b + k0));
+        VP.st(b + k0, rp_ + VP.ld(b + k0));
+        PP.st(b + k0 + 1, off + rp_);
+      }
+    }
+    if (in1) {
+      VA.st(b + k1, xn1 + VA.ld(b + k1));
+      if (r1) {
+        const double rv_ = h * c11, rp_ = h * h * (c21 - 0.5 * c11), off = p0q + h * (double)(k1 + 1) * v0q;
+        VJ.st(b + k1, (nx - xn1) * ih + VJ.ld(b + k1));
+        VV.st(b + k1, rv_ + VV.ld(b + k1));
+        VP.st(b + k1, rp_ + VP.ld(b + k1));
+        PP.st(b + k1 + 1, off + rp_);
+      }
+    }
+  }
+}
 #endif
 
 // ------------------------------------------------------------------ collision rows
@@ -734,6 +926,59 @@ SCP_DEV void collision_rows(Ctx& c, int want_res) {
   }
   SCP_SYNC(c);
 }
+
+#ifndef SCP_EMU
+// The collision rows of an iteration WITHOUT a residual check: the same update as collision_rows(c, 0) with the loads of
+// up to four candidate rows of a (step, agent) issued together (they come from L2: partner index, normal, bound, the
+// multiplier) before the first one is used, positions / forces through shared memory when they live there, and nothing
+// computed that only the residual check needs.
+template <bool SH>
+__device__ __forceinline__ void collision_rows_fast(Ctx& c) {
+  extern __shared__ double smem[];
+  const int K = c.K, N = c.N;
+  const HotView<SH> PP(c.a_P, smem), FF(c.a_F, smem);
+  const int* __restrict__ coff = c.wi + c.g->L.coff;
+  const int* __restrict__ cj = c.wi + c.g->L.c_j;
+  const double2* __restrict__ ceta = reinterpret_cast<const double2*>(c.wd + c.g->L.c_eta);
+  const double* __restrict__ cb = c.wd + c.g->L.c_bound;
+  double* lam = c.wd + c.g->L.lam;
+  const double hrho = 0.5 * c.rho;
+  const int items = (K - 1) * N, nt = blockDim.x;
+  const int dk = nt / N, di = nt - dk * N;
+  int k = 1 + (int)threadIdx.x / N, i = (int)threadIdx.x - (k - 1) * N;
+  for (int tI = threadIdx.x; tI < items; tI += nt) {
+    const int s0 = coff[k * N + i], s1 = coff[k * N + i + 1];
+    const double pix = PP.ld((2 * i) * K + k), piy = PP.ld((2 * i + 1) * K + k);
+    const double hrc = hrho * c.g->tb.rc[k - 1];
+    double* lrow = lam + ((size_t)k * N + i) * N;
+    double fx = 0.0, fy = 0.0;
+    for (int s = s0; s < s1; s += 4) {
+      int j[4]; double2 e[4]; double bd[4], l0[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int su = s + u < s1 ? s + u : s;
+        j[u] = cj[su]; e[u] = ceta[su]; bd[u] = cb[su];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) l0[u] = lrow[j[u]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s + u < s1) {
+          const double g = e[u].x * (pix - PP.ld((2 * j[u]) * K + k)) + e[u].y * (piy - PP.ld((2 * j[u] + 1) * K + k));
+          const double l1 = SCP_FMAX(0.0, l0[u] + hrc * (bd[u] - g));
+          lrow[j[u]] = l1;
+          const double f = 2.0 * l1 - l0[u];
+          fx += f * e[u].x; fy += f * e[u].y;
+        }
+      }
+    }
+    FF.st((2 * i) * K + k, fx); FF.st((2 * i + 1) * K + k, fy);
+    k += dk; i += di;
+    if (i >= N) { i -= N; ++k; }
+  }
+  __syncthreads();
+}
+#endif
 
 // Candidate rows.  flags[k][i][j] != 0 marks row (k,i,j) as carried by the ADMM.
 // mark_near_rows: start of a subproblem -- rows whose linearisation-point distance
@@ -1889,13 +2134,21 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
   const int pre_polish = (c.g->pb.polish && c.g->pb.polish_first) ? 1 : 0;
   for (int it = pre_polish ? 0 : 1; it <= maxit; ++it) {
     int want_polish = 0, chk = 0;          // rounds of the polish attempt this pass makes (0: none); residual check
+#ifdef SCP_PROFILE_SPLIT     // diagnostic build (make PROFILE_SPLIT=1): rel_step[29..31] of the record := cycles in fused
+    long long ts0 = 0;       // iterations, in their collision rows, in check iterations
+#endif
     double sc = 0.0, ss = 0.0, pri = 0.0, npri = 0.0, dua = 0.0, ndua = 0.0;
     if (it == 0) want_polish = c.g->pb.polish_first;
     else {
       chk = (it % check == 0) || it == maxit;
+#ifdef SCP_PROFILE_SPLIT
+      ts0 = SCP_CLOCK();
+#endif
 #ifndef SCP_EMU
       if (!chk && c.fused_epl > 0) {
-        admm_iter_fused<2>(c, c.fused_rows);
+        if (c.g->pb.team_mode == 3 || !c.mma_ok) admm_iter_fused<2>(c, c.fused_rows);   // warp-fused iteration (also: A/B timing)
+        else if (c.all_hot) admm_iter_mma<true>(c);
+        else admm_iter_mma<false>(c);
         __syncthreads();
       } else
 #endif
@@ -1904,11 +2157,25 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
         x_update(c, chk);
         forward_rows(c, 1, chk);
       }
+#ifdef SCP_PROFILE_SPLIT
+      const long long ts1 = SCP_CLOCK();
+      if (!chk) c.t_fused += ts1 - ts0;
+#endif
       double pri_col = 0.0;
       if (with_collisions && c.ncand > 0) {
-        collision_rows(c, chk);
-        if (chk) pri_col = reduce_finish(c, 0, 0);
+#ifndef SCP_EMU
+        if (!chk && c.fused_epl > 0 && c.g->pb.team_mode != 3) {
+          if (c.all_hot) collision_rows_fast<true>(c); else collision_rows_fast<false>(c);
+        } else
+#endif
+        {
+          collision_rows(c, chk);
+          if (chk) pri_col = reduce_finish(c, 0, 0);
+        }
       }
+#ifdef SCP_PROFILE_SPLIT
+      if (!chk) c.t_colx += SCP_CLOCK() - ts1;
+#endif
       o.iters = it;
       if (chk) {
         // ---- residuals in reference units (OSQP termination test, unscaled)
@@ -1972,6 +2239,9 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
         }
       }
     }
+#ifdef SCP_PROFILE_SPLIT
+    if (chk) c.t_chk += SCP_CLOCK() - ts0;
+#endif
     if (want_polish) {
       const long long t0 = SCP_CLOCK();
       polish_park(c, 0);
@@ -2082,7 +2352,7 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
 
   setup_scenario(c);
   c.rho = c.g->pb.rho0; c.copies = 0; c.ncand = 0; c.t_admm = 0; c.t_polish = 0; c.polish_rounds = 0; c.pol_valid = 0; c.pol_n = 0; c.pol_use_col = 0; c.pol_col_stale = 0; c.pol_no_smem = 0; c.pol_A = nullptr;
-  c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0;
+  c.t_pbuild = c.t_psolve = c.t_peval = c.t_papply = 0; c.t_fused = c.t_colx = c.t_chk = 0;
   const long long t_begin = SCP_CLOCK(), ns_begin = SCP_NANOS();
   double minsep; long long frow; double fdist;
   int feasible = 0, it = 0, converged = 0;
@@ -2178,6 +2448,9 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
   r.cycles_total += SCP_CLOCK() - t_begin; r.cycles_admm += c.t_admm; r.cycles_polish += c.t_polish; r.polish_rounds += c.polish_rounds;
   r.cycles_pbuild += c.t_pbuild; r.cycles_psolve += c.t_psolve; r.cycles_peval += c.t_peval; r.cycles_papply += c.t_papply;
   r.device_ns += SCP_NANOS() - ns_begin;
+#ifdef SCP_PROFILE_SPLIT
+  r.rel_step[29] += (double)c.t_fused; r.rel_step[30] += (double)c.t_colx; r.rel_step[31] += (double)c.t_chk;
+#endif
   if (resumable && r.status != SCP_B200_STATUS_INITIAL_QP_FAILED && it < c.g->pb.max_scp_iter && !converged && !feasible) {
     // suspend: the iterate goes to the scenario's acc output, the counters to its record
     r.reserved2 = 1;

@@ -300,18 +300,6 @@ def test_start_too_close_is_flagged(torch_cuda, lib):
     assert recs[0]["status"] == 2 and recs[0]["first_violation"] == (0, 0, 1)
 
 
-def test_golden_set_covers_binding_box_rows_and_config_sizes():
-    """the fixtures include a K=500 config-1 case, a 50-agent case and, per box class, a case where
-    that class binds at the certified optimum."""
-    names = [os.path.basename(p) for p in golden_cases()]
-    active = set()
-    for p in golden_cases():
-        active |= active_box_classes(np.load(p), tol=1e-6)
-    assert {"jerk", "acc", "vel", "pos"} <= active, active
-    assert any(int(np.load(p)["N"]) >= 50 for p in golden_cases()), names
-    assert any(round(float(np.load(p)["T"]) / float(np.load(p)["h"])) >= 500 for p in golden_cases()), names
-
-
 def test_c2_reference_outcomes_fixture(torch_cuda, lib):
     """The benchmark's own scenarios (config 2, seeds 10000..10063) against the outcomes of the VERBATIM reference at its
     own solver settings (tests/golden/c2_outcomes.npz, oracle/make_outcomes.py: OSQP defaults eps 1e-3, max_iter 10000,

@@ -135,3 +135,19 @@ def test_dynamics_residual_on_golden():
                                          positions=g["positions"])
         assert r <= 1e-8
         assert scp_oracle.min_separation(g["positions"]) >= float(g["R"]) - 0.01
+
+
+def test_golden_set_covers_binding_box_rows():
+    """per box class (jerk, acc, vel, pos) there is a fixture in which that class binds at the
+    KKT-certified optimum; every fixture carries certificates <= 1e-9."""
+    import os
+
+    from conftest import active_box_classes, golden_cases
+
+    active = {}
+    for p in golden_cases():
+        g = np.load(p)
+        assert float(np.max(g["certs"])) <= 1e-9, p
+        for cls in active_box_classes(g, tol=1e-6):
+            active.setdefault(cls, []).append(os.path.basename(p))
+    assert {"jerk", "acc", "vel", "pos"} <= set(active), active
