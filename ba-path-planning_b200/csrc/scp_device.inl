@@ -182,6 +182,7 @@ struct Ctx {
   double* hot_g[7];             // global homes
   int polish_rounds;            // add/drop rounds over all attempts of this scenario
   int pol_valid, pol_n, pol_use_col, pol_col_stale;   // polish list/inverse state carried between attempts
+  int pol_max_failed;           // failed polish attempts this subproblem may spend (halves with every unsolved subproblem of the scenario)
   long long t_pbuild, t_psolve, t_peval, t_papply;
   long long t_admm, t_polish;   // SM clock cycles spent in ADMM iterations / polish attempts
   long long t_fused, t_colx, t_chk;   // SCP_PROFILE_SPLIT builds only
@@ -2233,7 +2234,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
           const double gate = c.g->pb.polish_first_eps;
           const int settled = (sc == prev_sc && ss == prev_ss) && !(sc == fail_sc && ss == fail_ss);
           prev_sc = sc; prev_ss = ss;
-          if (settled && o.polish_attempts < c.g->pb.polish_max_failed &&
+          if (settled && o.polish_attempts < c.pol_max_failed &&
               pri <= gate * (1.0 + npri) && dua <= gate * (1.0 + ndua))
             want_polish = c.g->pb.polish_rounds;
         }
@@ -2398,6 +2399,14 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
         need_factor = !have_state || c.copies != old_copies;
       }
       if (need_factor) factor_operator(c);
+      // a scenario that already has unsolved subproblems is solver dependent from there on (scp.py:446-449) and its later
+      // subproblems are usually infeasible as well: each of them gets half the failed-polish budget of the one before
+      // (a failed attempt costs as much as ~170 ADMM iterations; one scenario of the 8192 of the 8-GPU bench spent 1.7 s there)
+      c.pol_max_failed = c.g->pb.polish_max_failed;
+      if (c.g->pb.cap_halving && !qp0) {
+        c.pol_max_failed >>= (r.qp_unsolved < 3 ? r.qp_unsolved : 3);
+        if (c.pol_max_failed < 1) c.pol_max_failed = 1;
+      }
       a = solve_qp(c, !qp0, !qp0 && (have_state || warm), qp0 ? 0 : r.qp_unsolved - r.qp_infeasible);   // QP #0 scp.py:138, QP #t scp.py:155
       have_state = 1;
       r.admm_iterations += a.iters;

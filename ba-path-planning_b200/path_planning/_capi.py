@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 MAX_SCP_ITER = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # in-tree build (csrc/Makefile -> ../lib); an installed package points SCP_B200_LIB at its copy
@@ -95,6 +95,12 @@ class Record(C.Structure):
     ]
 
 
+class Check(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "min_separation", "min_separation_step", "min_separation_continuous", "min_separation_continuous_time",
+        "box_violation", "dynamics_violation", "terminal_violation", "dynamics_residual")]
+
+
 STATUS_OK = 0
 STATUS_INITIAL_QP_FAILED = 1
 STATUS_START_TOO_CLOSE = 2
@@ -148,6 +154,16 @@ _SIGNATURES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          _P(C.c_float), _P(C.c_int64)],
+    ),
+    "scp_b200_generate_scenarios": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "scp_b200_check_batch": (
+        C.c_int,
+        [_P(Problem), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p],
     ),
     "scp_b200_linearize": (
         C.c_int,

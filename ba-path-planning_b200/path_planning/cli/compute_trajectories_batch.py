@@ -78,7 +78,7 @@ def load_config(path):
         data = yaml.safe_load(f) or {}
     if not isinstance(data, dict):
         raise ValueError(f"{path}: expected a mapping of CONFIG keys")
-    unknown = sorted(set(data) - set(CONFIG) - {"engine"})
+    unknown = sorted(set(data) - set(CONFIG) - {"engine", "analysis"})
     if unknown:
         raise ValueError(f"{path}: unknown config keys {unknown}; known: {sorted(CONFIG)}")
     return data
@@ -133,8 +133,15 @@ def run_batch(N, cfg, n_trials, seeds=None):
         solver = BatchSolver(N, cfg["time_horizon"], cfg["time_step"], cfg["min_distance"], cfg["space_dims"],
                              max_scp_iter=cfg["max_iterations"])
     t0 = time.perf_counter()
-    _, recs = solver.solve(np.stack(starts), np.stack(goals))
+    traj, recs = solver.solve(np.stack(starts), np.stack(goals))
     dt = time.perf_counter() - t0
+    checks = [None] * n_trials
+    if cfg.get("analysis", True) and traj and "positions" in traj:
+        # post-solve analysis on the device (outside time_sec): continuous-time separation and dynamics residual
+        from ..analysis import check_trajectories
+
+        checks = check_trajectories(traj, np.stack(starts), np.stack(goals), cfg["time_step"], cfg["space_dims"],
+                                    min_distance=cfg["min_distance"])
     # copies of one trial: 4 (N,2) inputs up, 3 (N,K,2) outputs + the record down, at the PCIe rate the batch saw
     # (bounded by what is left of the wall time after the longest scenario)
     longest = max(r["device_ns"] for r in recs) * 1e-9
@@ -149,6 +156,8 @@ def run_batch(N, cfg, n_trials, seeds=None):
             "batch_time_sec": dt, "device_time_sec": r["device_ns"] * 1e-9, "seed": used[t], "rank": rank,
             "scp_iterations": r["scp_iterations"], "admm_iterations": r["admm_iterations"],
             "qp_unsolved": r["qp_unsolved"], "min_separation": r["min_separation"],
+            "min_separation_continuous": checks[t]["min_separation_continuous"] if checks[t] else None,
+            "dynamics_residual": checks[t]["dynamics_residual"] if checks[t] else None,
         })
     return gather_records(out) if world > 1 else out
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCP_B200_ABI_VERSION 3
+#define SCP_B200_ABI_VERSION 4
 #define SCP_B200_MAX_SCP_ITER 32
 
 /* Problem definition shared by every scenario of a batch.
@@ -178,6 +178,41 @@ int scp_b200_linearize(const double* d_pos, int n_scenarios, int n_agents, int n
 int scp_b200_linearize_range(const double* d_pos, int n_scenarios, int n_agents, int n_steps,
                              double min_distance, double feas_margin, int64_t pair_begin, int64_t pair_end,
                              double* d_eta, double* d_bound, double* d_minsep, int32_t* d_first, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The steps either side of the solve.
+ *
+ * scp_b200_generate_scenarios: batched rejection-sampling scenario generator on the device -- the construction and
+ * acceptance rules of reference scenarios/position_generator.py:44-75 (layout 0: starts on the four corner circles,
+ * goals on the central diamond / circles of the 20 x 20 m box, pairwise spacing >= min_distance, max_attempts draws
+ * per set, default 1000) or of the bounded-travel generator used beyond 50 agents (layout 1: arena side sqrt(16 N),
+ * spacing 1.25 R, travel 0.5..1 x 0.4 v_max T; default 200 N attempts).  Scenario b draws from a counter-based
+ * stream keyed by (seed, first_scenario + b): reproducible, but NOT the host generator's Mersenne-twister draws.
+ *   d_p0, d_pf : (B,N,2) out;  d_status : (B) int32 out, 1 = placed, 0 = attempts exhausted (the reference raises
+ *   ValueError, position_generator.py:58-59, 72-73). */
+int scp_b200_generate_scenarios(int n_scenarios, int n_agents, int layout, double min_distance, double time_horizon,
+                                double vel_limit, uint64_t seed, int first_scenario, int max_attempts, double* d_p0,
+                                double* d_pf, int32_t* d_status, void* stream);
+
+/* Post-solve analysis of B trajectories (result dict scp.py:171-175): the minimum separation at the samples (the
+ * quantity _fast_check_avoidance_constraints tests, scp.py:597-615, and print_distance_analysis reports,
+ * position_generator.py:173-205), the minimum separation in CONTINUOUS time (piecewise-constant acceleration between
+ * samples, scp.py:371-397: closed-form minimum of the quartic |d(t)|^2 on every interval), and the dynamics residual
+ * of SURVEY.md 8(c): box rows on states 1..K-1 (scp.py:188-257), state recursion between consecutive samples,
+ * terminal equalities on state K. */
+typedef struct scp_b200_check {
+  double min_separation;                 /* min over k in [0,K), i<j of ||p_i[k] - p_j[k]|| */
+  double min_separation_step;            /* the k where it is attained */
+  double min_separation_continuous;      /* min over t in [0,(K-1)h], i<j */
+  double min_separation_continuous_time; /* the t where it is attained (seconds) */
+  double box_violation;                  /* max violation of the jerk / acc / vel / pos boxes, >= 0 */
+  double dynamics_violation;             /* max |state[k+1] - step(state[k], a[k])| and |state[0] - initial state| */
+  double terminal_violation;             /* max |state[K] - final state| */
+  double dynamics_residual;              /* max of the three: pass iff <= 1e-3 */
+} scp_b200_check;
+int scp_b200_check_batch(const scp_b200_problem* prob, int n_scenarios, const double* d_acc, const double* d_pos,
+                         const double* d_vel, const double* d_p0, const double* d_v0, const double* d_pf,
+                         const double* d_vf, scp_b200_check* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Streaming solver: the same loop (scp.py:131-180) as a fixed sequence of HBM/L2-streaming kernels
