@@ -1316,7 +1316,36 @@ SCP_DEV void sp_decode(long long e, int& i, int& j) {
 }
 
 // A_ij += s v_i v_j over the packed lower triangle of an n x n matrix, skipping row/column `skip` (-1: none)
+#ifndef SCP_EMU
+// One warp per row of the packed triangle (rows dealt cyclically to the warps, lanes along the row): no index decoding,
+// conflict-free, and -- SH: A and v live in shared memory -- LDS/STS through the dynamic shared array instead of generic
+// loads (ncu, round 2: the flat decode loop was 13 % of the solver's samples, 58 % of them long-scoreboard stalls).
+template <bool SH>
+__device__ __forceinline__ void sp_rank1_rows(double* A, int n, const double* v, double s, int skip) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int oa = SH ? (int)(A - smem) : 0, ov = SH ? (int)(v - smem) : 0;
+  for (int i = threadIdx.x >> 5; i < n; i += nw) {
+    if (i == skip) continue;
+    const double svi = s * (SH ? smem[ov + i] : v[i]);
+    const int r = (int)sp_row(i);
+    for (int j = lane; j <= i; j += 32) {
+      if (j == skip) continue;
+      if (SH) smem[oa + r + j] += svi * smem[ov + j];
+      else A[r + j] += svi * v[j];
+    }
+  }
+  __syncthreads();
+}
+#endif
 SCP_DEV void sp_rank1(Ctx& c, double* A, int n, const double* v, double s, int skip) {
+#ifndef SCP_EMU
+  if (c.team == 1) {
+    if (__isShared(A) && __isShared(v)) sp_rank1_rows<true>(A, n, v, s, skip);
+    else sp_rank1_rows<false>(A, n, v, s, skip);
+    return;
+  }
+#endif
   const long long total = (long long)sp_row(n);
   SCP_PHASE(c) {
     for (long long e = tid; e < total; e += c.nthreads) {
@@ -1333,7 +1362,22 @@ SCP_DEV void sp_rank1(Ctx& c, double* A, int n, const double* v, double s, int s
 SCP_DEV void sp_matvec(Ctx& c, const double* A, int n, const double* x, double* out, int accumulate) {
 #ifndef SCP_EMU
   if (c.team == 1) {
+    extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (__isShared(A) && __isShared(x)) {          // shared-memory operands: LDS with 32-bit addresses
+      const int oa = (int)(A - smem), ox = (int)(x - smem);
+      for (int i = threadIdx.x >> 5; i < n; i += nw) {
+        const int r = oa + (int)sp_row(i);
+        double a = 0.0;
+        for (int j = lane; j <= i; j += 32) a += smem[r + j] * smem[ox + j];
+        for (int j = i + 1 + lane; j < n; j += 32) a += smem[oa + (int)sp_row(j) + i] * smem[ox + j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) out[i] = (accumulate ? out[i] : 0.0) + a;
+      }
+      __syncthreads();
+      return;
+    }
     for (int i = threadIdx.x >> 5; i < n; i += nw) {
       const double* row = A + sp_row(i);
       double a = 0.0;

@@ -38,6 +38,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CFG = dict(N=25, T=10.0, h=0.2, R=0.8, space=[0, 0, 20, 20], max_iterations=15)
+# other sizes, e.g. config 1: SCP_OUTCOME_CFG='{"N": 10, "T": 100.0, "space": [0, 0, 200, 200]}' SCP_OUTCOME_SEEDS=0
+CFG.update(json.loads(os.environ.get("SCP_OUTCOME_CFG", "{}")))
 MAXQ = 16          # QP #0 + at most 15 avoidance QPs
 
 
