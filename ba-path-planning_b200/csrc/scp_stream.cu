@@ -553,7 +553,10 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   const int ia = d.a_lo + blockIdx.x * apc, ib = min(ia + apc, d.a_hi);
   const int ax = warp & 1;                                    // two warps per agent: one per axis
   double* Nm = sm;
-  double* myrhs = sm + (size_t)K * K + 4 + (size_t)warp * (K + (K & 1));   // 4 doubles of padding behind the operator
+  const int Kr = K + (K & 1);
+  double* rhs_rows = sm + (size_t)K * K + 4;                                // 4 doubles of padding behind the operator
+  double* myrhs = rhs_rows + (size_t)warp * Kr;
+  double* xout = rhs_rows + (size_t)(blockDim.x >> 5) * Kr;                 // [8 right-hand sides][Kr]: N rhs, written by the tensor-pipe product
   constexpr bool vec = VEC != 0;      // K even: rows are 16-byte aligned and move as double2 (compile time: no dual code paths)
   if (threadIdx.x < 4) sm[(size_t)K * K + threadIdx.x] = 0.0;
   // operator -> shared memory: ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by thread 0 when
@@ -608,8 +611,14 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
   }
   double pr = 0.0, nr = 0.0, voj = 0.0, voa = 0.0, vov = 0.0, vop = 0.0, worst = 0.0;
   bool staged = false;
-  for (int i = ia + (warp >> 1); i < ib || !staged; i += npair) {
-    const bool live = i < ib;      // every warp passes the staging barrier once, even without an agent of its own
+  // Rounds are uniform over the CTA (the operator product of a round is a block-wide tensor-pipe GEMM over the CTA's
+  // eight agent-axes): a warp without an agent of its own in a round recomputes the CTA's first agent and stores nothing.
+  const int rounds = (ib - ia + npair - 1) / npair;
+  for (int rnd = 0; rnd < rounds; ++rnd) {
+    const int i_raw = ia + (warp >> 1) + rnd * npair;
+    const bool live = i_raw < ib;
+    const int i = live ? i_raw : ia;
+    const double pr_s = pr, nr_s = nr, voj_s = voj, voa_s = voa, vov_s = vov, vop_s = vop;   // a recomputed agent adds nothing
     // ---- 1. collision rows of agent i: this axis' component of the force on state k (fz[e] <-> state k0+e).
     // Both axis warps walk the rows and compute the same multipliers; the x warp stores them (other buffer).
     double fz[EPL], fyo[EPL];
@@ -694,7 +703,6 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
       }
       staged = true;
     }
-    if (!live) break;
     // ---- 2. this warp's axis of agent i
     {
       const int q = 2 * i + ax;
@@ -718,7 +726,7 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
         // own row of the other buffer still holds the positions of two iterations ago; forces of the last one are in F
         double fold[EPL];
         load_row<EPL>(d.F + row, k0, K, vec, fold);
-        store_row<EPL>(d.F + row, k0, K, vec, fz);
+        if (live) store_row<EPL>(d.F + row, k0, K, vec, fz);
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           const int k = k0 + e;
@@ -755,35 +763,43 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
         const double prev = e == 0 ? wprev : wj[e == 0 ? 0 : e - 1];
         if (k < K) myrhs[k] = sig * xo[e] + (prev - wj[e]) * ih + wa[e] + h * r1v[e] + h * h * (r2p[e] - 0.5 * r1p[e]);
       }
-      __syncwarp();
-      // x = Nmat rhs + N0 d : lane owns EPL adjacent columns of the symmetric operator (zeros beyond K)
+      // x = Nmat rhs + N0 d for the CTA's eight agent-axes at once on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA):
+      // M = K steps in tiles of 8 (tiles `warp` and `warp + 8` of this warp, two accumulator chains in flight), N = the 8
+      // right-hand-side rows, K-dimension in steps of 4.  Operand rows K..Kr-1 / steps beyond K are masked to zero.
       const double d0 = d.vf[q2] - v0q, d1 = d.pf[q2] - (p0q + h * (double)K * v0q);
-      double a0[EPL], a1[EPL];
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) { a0[e] = 0.0; a1[e] = 0.0; }
+      __syncthreads();
       {
-        // lanes beyond K read column 0 (discarded below); a lane straddling K reads into the next row / the padding
-        const int kc = (k0 < K) ? k0 : 0;
-        const double* np = Nm + kc;
-        int j = 0;
-#pragma unroll 2
-        for (; j + 1 < K; j += 2) {
-          const double r0 = myrhs[j], r1 = myrhs[j + 1];
-          double n0[EPL], n1[EPL];
-          load_row_nc<EPL>(np, 0, vec, n0);
-          load_row_nc<EPL>(np + K, 0, vec, n1);
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) { a0[e] += n0[e] * r0; a1[e] += n1[e] * r1; }
-          np += 2 * K;
-        }
-        if (j < K) {
-          const double r0 = myrhs[j];
-          double n0[EPL];
-          load_row_nc<EPL>(np, 0, vec, n0);
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) a0[e] += n0[e] * r0;
+        const int g = lane >> 2, t = lane & 3, nw8 = blockDim.x >> 5;
+        const int MT = (K + 7) >> 3;
+        const int m0 = warp * 8 + g, m1 = (warp + nw8) * 8 + g;
+        const bool has1 = warp + nw8 < MT;
+        const double* a0p = Nm + (size_t)(m0 < K ? m0 : K - 1) * K;
+        const double* a1p = Nm + (size_t)(m1 < K ? m1 : K - 1) * K;
+        const double* bp = rhs_rows + (size_t)g * Kr;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        if (warp < MT) {
+          for (int kk = 0; kk < K; kk += 4) {
+            const int ka = kk + t;
+            const bool in = ka < K;
+            const int kc = in ? ka : K - 1;
+            const double bv = in ? bp[kc] : 0.0;
+            const double av0 = in ? a0p[kc] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c00), "+d"(c01) : "d"(av0), "d"(bv));
+            if (has1) {
+              const double av1 = in ? a1p[kc] : 0.0;
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(c10), "+d"(c11) : "d"(av1), "d"(bv));
+            }
+          }
+          if (m0 < K) { xout[(size_t)(2 * t) * Kr + m0] = c00; xout[(size_t)(2 * t + 1) * Kr + m0] = c01; }
+          if (has1 && m1 < K) { xout[(size_t)(2 * t) * Kr + m1] = c10; xout[(size_t)(2 * t + 1) * Kr + m1] = c11; }
         }
       }
+      __syncthreads();
+      double a0[EPL], a1[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { const int k = k0 + e; a0[e] = (k < K) ? xout[(size_t)warp * Kr + k] : 0.0; a1[e] = 0.0; }
       double xn[EPL], c1[EPL], c2[EPL];
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
@@ -797,8 +813,10 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
         m0 = warp_sum(m0); m1 = warp_sum(m1);
         if (lane == 0) {
           const double* gg = d.gg + (size_t)b * 4;
-          d.mu[((size_t)b * d.Qs + q) * 2] = m0 - (gg[0] * d0 + gg[1] * d1);
-          d.mu[((size_t)b * d.Qs + q) * 2 + 1] = m1 - (gg[1] * d0 + gg[2] * d1);
+          if (live) {
+            d.mu[((size_t)b * d.Qs + q) * 2] = m0 - (gg[0] * d0 + gg[1] * d1);
+            d.mu[((size_t)b * d.Qs + q) * 2 + 1] = m1 - (gg[1] * d0 + gg[2] * d1);
+          }
         }
       }
       __syncwarp();
@@ -823,8 +841,8 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
             nvj[e] = ((on & 1) ? alpha : 1.0) * aj + sj[e];
             nvv[e] = ((on & 4) ? alpha : 1.0) * rv_ + sv[e];
             nvp[e] = ((on & 8) ? alpha : 1.0) * rp_ + sp[e];
-            Pn[(size_t)q * K + k + 1] = off[e] + rp_;
-            if (d.p2p) {   // the own slice goes straight into every peer's buffer over NVLink (B = 1 when sharded)
+            if (live) Pn[(size_t)q * K + k + 1] = off[e] + rp_;
+            if (d.p2p && live) {   // the own slice goes straight into every peer's buffer over NVLink (B = 1 when sharded)
               for (int g = 0; g < d.G; ++g)
                 if (g != d.rank) (cur ? d.peerP[g] : d.peerP1[g])[(size_t)q * K + k + 1] = off[e] + rp_;
             }
@@ -839,14 +857,18 @@ __device__ __forceinline__ void iter_body(const Dev& d, const State& S, int apc,
           }
         }
       }
-      store_row<EPL>(d.x + row, k0, K, vec, xn);
-      if (BOX) {
-        if (on & 2) store_row<EPL>(d.va + row, k0, K, vec, nva);
-        if (on & 1) store_row<EPL>(d.vj + row, k0, K, vec, nvj);
-        if (on & 4) store_row<EPL>(d.vv + row, k0, K, vec, nvv);
-        if (on & 8) store_row<EPL>(d.vp + row, k0, K, vec, nvp);
+      if (live) {
+        store_row<EPL>(d.x + row, k0, K, vec, xn);
+        if (BOX) {
+          if (on & 2) store_row<EPL>(d.va + row, k0, K, vec, nva);
+          if (on & 1) store_row<EPL>(d.vj + row, k0, K, vec, nvj);
+          if (on & 4) store_row<EPL>(d.vv + row, k0, K, vec, nvv);
+          if (on & 8) store_row<EPL>(d.vp + row, k0, K, vec, nvp);
+        }
+        if (CHK) store_row<EPL>(d.FY + row, k0, K, vec, fyo);
+      } else if (CHK) {
+        pr = pr_s; nr = nr_s; voj = voj_s; voa = voa_s; vov = vov_s; vop = vop_s;
       }
-      if (CHK) store_row<EPL>(d.FY + row, k0, K, vec, fyo);
       __syncwarp();
     }
   }
@@ -1616,7 +1638,7 @@ int scp_b200_stream_create(const scp_b200_problem* prob, int n_scenarios, int ma
     int apc = Nown > 0 ? (Nown + nba - 1) / nba : nwarp;
     apc = ((apc + nwarp - 1) / nwarp) * nwarp;
     s->apc = apc; s->nblk_a = Nown > 0 ? (Nown + apc - 1) / apc : 1;
-    s->smem_iter = ((size_t)K * K + 4 + (size_t)(ss::IT_THREADS / 32) * (K + (K & 1))) * sizeof(double);
+    s->smem_iter = ((size_t)K * K + 4 + 2 * (size_t)(ss::IT_THREADS / 32) * (K + (K & 1))) * sizeof(double);   // operator, rhs rows, product rows
     set_axis_smem(ss::k_iter<1, 0>, s->smem_iter); set_axis_smem(ss::k_iter<1, 1>, s->smem_iter);
     set_axis_smem(ss::k_iter<2, 0>, s->smem_iter); set_axis_smem(ss::k_iter<2, 1>, s->smem_iter);
     set_axis_smem(ss::k_iter<3, 0>, s->smem_iter); set_axis_smem(ss::k_iter<3, 1>, s->smem_iter);

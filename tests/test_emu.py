@@ -3,7 +3,7 @@ against the certified golden fixtures.  The same source runs on the GPU in test_
 import numpy as np
 import pytest
 
-from conftest import golden_cases
+from conftest import golden_cases, golden_limits
 
 emu = pytest.importorskip("emu_binding")
 
@@ -11,7 +11,7 @@ emu = pytest.importorskip("emu_binding")
 @pytest.mark.parametrize("path", golden_cases(max_agents=8))
 def test_emulated_kernel_matches_golden(path):
     g = np.load(path)
-    tr, recs = emu.solve(g["p0"], g["pf"], float(g["T"]), float(g["h"]), float(g["R"]), list(g["space"]))
+    tr, recs = emu.solve(g["p0"], g["pf"], float(g["T"]), float(g["h"]), float(g["R"]), list(g["space"]), **golden_limits(g))
     r = recs[0]
     assert r["status"] == 0 and r["scp_iterations"] == int(g["iterations"])
     assert np.allclose(r["rel_steps"], g["rel_steps"], rtol=5e-3, atol=1e-4)

@@ -4,7 +4,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import golden_cases
+from conftest import golden_cases, golden_limits
 from oracle import scenarios, scp_oracle
 
 
@@ -68,6 +68,8 @@ def test_T4_exactly_4N_equalities():
 def test_generator_matches_golden_inputs():
     for f in golden_cases():
         g = np.load(f)
+        if int(g["seed"]) < 0:
+            continue                     # explicit start/goal positions (binding box-row cases), not generated
         random.seed(int(g["seed"]))
         p0, pf = scenarios.generate_positions(int(g["N"]), float(g["R"]))
         assert np.array_equal(p0, g["p0"]) and np.array_equal(pf, g["pf"])
@@ -96,6 +98,10 @@ def test_oracle_reproduces_golden(path, truth_mode):
     g = np.load(path)
     N = int(g["N"])
     o = scp_oracle.ScpOracle(N, float(g["T"]), float(g["h"]), float(g["R"]), list(g["space"]))
+    for key, val in golden_limits(g).items():            # box limits are plain attributes, as in the reference (scp.py:67-74)
+        name = key.split("_")[0]
+        setattr(o, name + "_min", -val)
+        setattr(o, name + "_max", val)
     o.set_initial_states(g["p0"])
     o.set_final_states(g["pf"])
     tr = o.generate_trajectories()
