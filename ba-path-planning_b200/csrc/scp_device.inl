@@ -2155,12 +2155,12 @@ SCP_DEV void active_signature(Ctx& c, int with_collisions, double* count, double
 }
 
 // ------------------------------------------------------------------ ADMM
-struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua; };
+struct AdmmOut { int iters; int solved; int certified; int infeasible; int polish_attempts; double pri, dua, npri, ndua; };
 // a subproblem whose active set keeps cycling stops asking for the polish after pb.polish_max_failed failed attempts and
 // ends on the ADMM residual test instead (a few scenarios spent > 50 attempts x 40 rounds: the tail of a batch)
 
 SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps_abs, double eps_rel, int maxit) {
-  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY;
+  AdmmOut o; o.iters = 0; o.solved = 0; o.certified = 0; o.infeasible = 0; o.polish_attempts = 0; o.pri = o.dua = INFINITY; o.npri = o.ndua = 0.0;
   const int K = c.K;
   double* red = c.sh;
   double* x = c.a_x;
@@ -2260,7 +2260,7 @@ SCP_DEV AdmmOut admm_run(Ctx& c, int with_collisions, int keep_state, double eps
         SCP_SYNC(c);
         dua = reduce_finish(c, 0, 0);
         ndua = reduce_finish(c, 1, 0);
-        o.pri = pri; o.dua = dua;
+        o.pri = pri; o.dua = dua; o.npri = npri; o.ndua = ndua;
         if (pri <= eps_abs + eps_rel * npri && dua <= eps_abs + eps_rel * ndua) { o.solved = 1; break; }
         if (!(pri == pri) || !(dua == dua)) break;   // NaN guard
         if (it >= 4 * check && primal_infeasible(c, with_collisions)) { o.infeasible = 1; break; }
@@ -2465,7 +2465,10 @@ SCP_DEV int solve_scenario(Ctx& c, int resumable) {
     r.polish_attempts += a.polish_attempts;
     r.pri_res = a.pri; r.dua_res = a.dua;
     if (qp0) {
-      if (!a.solved) { r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; r.qp_unsolved++; }
+      // scp.py:363-365 raises unless OSQP reports "solved" or "solved inaccurate" (status_val 1 or 2): an initial QP that
+      // ends at its iteration cap within 10x of OSQP's default tolerances (eps 1e-3) is accepted like status 2
+      const int inaccurate_ok = !a.infeasible && a.pri <= 10.0 * (1e-3 + 1e-3 * a.npri) && a.dua <= 10.0 * (1e-3 + 1e-3 * a.ndua);
+      if (!a.solved) { r.qp_unsolved++; if (!inaccurate_ok) r.status = SCP_B200_STATUS_INITIAL_QP_FAILED; }
       forward_rows(c, 0);                                 // positions of the initial guess, scp.py:140
       gate_and_minsep(c, &minsep, &frow, &fdist);         // scp.py:144
       feasible = frow < 0;
