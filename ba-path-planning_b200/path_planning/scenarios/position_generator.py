@@ -120,3 +120,26 @@ def generate_positions_large(n_vehicles, min_distance=0.8, time_horizon=20.0, ve
     if n < n_vehicles:
         raise ValueError("Could not generate enough positions.")
     return starts, goals, [0.0, 0.0, side, side]
+
+
+def print_distance_analysis(initial_positions, final_positions):
+    """Distance report of a start/goal set (reference position_generator.py:173-205): smallest pairwise spacing over
+    both sets and the longest straight-line trip; same printed block and returned keys.  The per-trajectory counterpart
+    (sampled and continuous-time separation of a SOLVED scenario) is `path_planning.analysis.check_trajectories`."""
+    a = np.asarray(initial_positions, dtype=float)
+    b = np.asarray(final_positions, dtype=float)
+
+    def closest(points):
+        if len(points) < 2:
+            return float("inf")
+        i, j = np.triu_indices(len(points), 1)
+        return float(np.linalg.norm(points[i] - points[j], axis=1).min())
+
+    trips = np.linalg.norm(b - a, axis=1)
+    report = dict(global_min_distance=min(closest(a), closest(b)), longest_path=trips.max(), longest_vehicle=trips.argmax())
+    bar = "=" * 40
+    print(f"\n{bar}\nDISTANCE SUMMARY\n{bar}")
+    print(f"Global minimum distance: {report['global_min_distance']:.3f} m")
+    print(f"Longest path traveled:  {report['longest_path']:.3f} m (Vehicle {report['longest_vehicle']})")
+    print(bar + "\n")
+    return report

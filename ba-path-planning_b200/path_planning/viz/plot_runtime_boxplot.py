@@ -31,3 +31,27 @@ def make_boxplot(csv_path, save_path=None, show=False):
     if show:
         plt.show()
     return by_n
+
+
+# same module-level configuration and zero-argument entry point as the reference (plot_runtime_boxplot.py:19-22, 118-120)
+CONFIG = {
+    "data_dir": "results/trial_2",          # folder with scp_benchmark_*.csv
+    "out_path": "plots/scp_boxplot.pdf",    # where to save the plot
+}
+
+
+def main():
+    import glob
+    import os
+
+    files = sorted(glob.glob(os.path.join(CONFIG["data_dir"], "scp_benchmark_*.csv")))
+    if not files:
+        raise FileNotFoundError(f"No 'scp_benchmark_*.csv' files in {CONFIG['data_dir']}")
+    merged = {}
+    for fp in files:
+        for n, ts in read_times(fp).items():
+            merged.setdefault(n, []).extend(ts)
+    os.makedirs(os.path.dirname(CONFIG["out_path"]) or ".", exist_ok=True)
+    make_boxplot(files[-1], save_path=CONFIG["out_path"])
+    print(f"Saved plot: {CONFIG['out_path']}")
+    return merged

@@ -106,3 +106,28 @@ def test_stream_create_argument_errors_without_gpu():
     assert b"ONE scenario" in lib.scp_b200_last_error()
     assert lib.scp_b200_stream_create(C.byref(p), 1, 16, 3, 2, None, C.byref(h)) != 0      # rank outside world
     assert h.value is None
+
+
+def test_analysis_and_device_generator_have_no_cpu_path():
+    """The steps either side of the solve (scp_b200_check_batch, scp_b200_generate_scenarios) are device kernels:
+    without a CUDA device the host wrappers raise, they do not fall back to numpy."""
+    import numpy as np
+    import torch
+
+    from path_planning import _capi
+    from path_planning.analysis import FIELDS, check_trajectories
+    from path_planning.scenarios.device_generator import generate_scenarios_device, space_dims_for
+
+    assert C.sizeof(_capi.Check) == 8 * len(FIELDS) == 64
+    assert space_dims_for("reference", 25) == [0.0, 0.0, 20.0, 20.0] and abs(space_dims_for("large", 100)[2] - 40.0) < 1e-12
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    z = np.zeros((2, 5, 2))
+    with pytest.raises(_capi.ScpB200Error):
+        check_trajectories({"positions": z, "velocities": z, "accelerations": z}, z[:, 0], z[:, 0], 0.2)
+    with pytest.raises(_capi.ScpB200Error):
+        generate_scenarios_device(4, 10, 0.8)
+    # argument errors are reported through the C ABI without touching the GPU
+    lib = _capi.load()
+    assert lib.scp_b200_generate_scenarios(1, 0, 0, 0.8, 10.0, 2.0, 0, 0, 0, None, None, None, None) != 0
+    assert lib.scp_b200_check_batch(None, 1, None, None, None, None, None, None, None, None, None) != 0

@@ -268,3 +268,20 @@ def test_bench_parity_block_on_the_fixture_itself():
         assert abs(bench.dynamics_residual(a, p, f["p0"][b], f["pf"][b], 0.2, [0, 0, 20, 20])
                    - scp_oracle.dynamics_residual(a, f["p0"][b], z, f["pf"][b], z, 0.2, [0, 0, 20, 20], positions=p)) <= 1e-12
         assert abs(bench.min_separation(p) - scp_oracle.min_separation(p)) <= 1e-15
+
+
+def test_pyproject_declares_the_reference_console_scripts():
+    """reference pyproject.toml:52-54: the entrypoint names of this path exist after `pip install`."""
+    import importlib
+    import tomllib
+
+    from conftest import ROOT
+
+    cfg = tomllib.load(open(os.path.join(ROOT, "pyproject.toml"), "rb"))
+    scripts = cfg["project"]["scripts"]
+    assert scripts["compute-trajectories"] == "path_planning.cli.compute_trajectories:main"
+    assert scripts["compute-trajectories-batch"] == "path_planning.cli.compute_trajectories_batch:main"
+    for target in scripts.values():
+        mod, fn = target.split(":")
+        assert callable(getattr(importlib.import_module(mod), fn))
+    assert cfg["tool"]["setuptools"]["packages"]["find"]["where"] == ["ba-path-planning_b200"]

@@ -42,6 +42,21 @@ def test_product_generator_bit_exact(ref):
         generate_positions(200, 0.8)
 
 
+def test_product_distance_report_equals_reference(ref, capsys):
+    """print_distance_analysis (reference position_generator.py:173-205): same numbers, same printed block."""
+    from path_planning.scenarios.position_generator import generate_positions, print_distance_analysis
+
+    random.seed(3)
+    p0, pf = generate_positions(20, 0.8)
+    with ref_loader.quiet() as buf:
+        want = ref.scenarios.position_generator.print_distance_analysis(p0, pf)
+    got = print_distance_analysis(p0, pf)
+    out = capsys.readouterr().out
+    assert abs(got["global_min_distance"] - want["global_min_distance"]) <= 1e-15
+    assert abs(got["longest_path"] - want["longest_path"]) <= 1e-15 and int(got["longest_vehicle"]) == int(want["longest_vehicle"])
+    assert out.strip().splitlines() == buf.getvalue().strip().splitlines()
+
+
 def test_matrices_and_rows_equal(ref):
     N = 6
     random.seed(3)
